@@ -1,0 +1,28 @@
+"""CPU oracle for the MDIMG deterministic image hot path.  TEST INFRASTRUCTURE ONLY.
+
+This package restates, in numpy + scipy, the arithmetic that the reference's
+``pipeline/enhancement.py`` and ``pipeline/metrics.py`` delegate to scikit-image,
+PyWavelets, scipy.ndimage and numpy.  It exists to check the CUDA path; it is never
+the product path.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it.
+
+PARITY STATUS
+-------------
+* scipy.ndimage (``uniform_filter``, ``gaussian_filter``, ``convolve``) and numpy
+  (``percentile``, ``histogram``, ``median``, reductions) are *called directly* — for
+  those routines this oracle IS the reference's own arithmetic.
+* scikit-image and PyWavelets are un-vendored third-party dependencies of the reference
+  (``requirements.txt:2-6``: scikit-image>=0.21, PyWavelets>=1.4, only lower-bounded) and
+  are NOT installed in the build container (no network).  Their routines are restated
+  from their published algorithms (skimage 0.21-0.25 ``restoration/_denoise.py``,
+  ``exposure/_adapthist.py``, ``exposure/exposure.py``, ``filters/edges.py``,
+  ``filters/_unsharp_mask.py``, ``metrics/_structural_similarity.py``; pywt 1.4-1.8
+  ``_multilevel.py``, ``_thresholding.py``, ``c/convolution.template.c``).  The
+  reference's own tests hold no golden vectors or known-answer values for this path
+  (``tests/test_metrics.py``, ``tests/test_pipeline.py`` assert shapes/keys/ranges only),
+  so for the skimage/pywt-backed routines the status is **parity unpinned**: the
+  restatement is checked against mathematical identities (perfect reconstruction,
+  orthogonality, hand-computed answers), cv2 cross-checks and the reference's own
+  property tests, not against outputs of a real skimage/pywt install.
+* numpy semantics follow numpy >= 2 (NEP 50 promotion), which is what is installed.
+"""

@@ -1,0 +1,165 @@
+/* mdimg_b200 — C ABI of the B200-native MDIMG image hot path (libmdimg_b200.so).
+ *
+ * The reference (Hiresh444/medical-image-enhancer) has no FFI: its hot path is a set of plain
+ * Python functions in pipeline/enhancement.py, pipeline/metrics.py and pipeline/dicom_io.py that
+ * call scikit-image / PyWavelets / scipy.  Each entry point below names the reference function
+ * (file:line under /root/reference) whose arithmetic it replaces; the Python shim in
+ * medical-image-enhancer_b200/ binds them with ctypes and re-exposes the reference's own
+ * function signatures.
+ *
+ * Conventions
+ *  - every image argument is a DEVICE pointer to an [n][h][w] contiguous stack of 2-D slices
+ *    (float32 normalised to [0,1] unless stated otherwise); slices are independent;
+ *  - `sel` (device int32[n_sel], may be NULL) restricts the call to a subset of slices; outputs
+ *    indexed by slice keep their position in the full stack;
+ *  - the caller owns all buffers; scratch memory is a caller-provided device workspace whose
+ *    size is queried with mdimg_workspace_bytes(); nothing is allocated behind the caller's back
+ *    except one pinned int per mdimg_tv_chambolle call;
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream unless
+ *    noted; results in device memory are valid after the stream is synchronised;
+ *  - every function returns MDIMG_OK (0) or an error code; mdimg_last_error() returns a
+ *    thread-local message.  There is NO CPU fallback: without an sm_100 device mdimg_init fails.
+ */
+#ifndef MDIMG_B200_H
+#define MDIMG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDIMG_OK 0
+#define MDIMG_ERR_INVALID 1
+#define MDIMG_ERR_CUDA 2
+#define MDIMG_ERR_WORKSPACE 3
+#define MDIMG_ERR_NO_DEVICE 4
+
+/* Result-row layout of mdimg_metrics (doubles per slice). Columns 0..15 are the 16 metrics in the
+ * key order of compute_metrics' dict (pipeline/metrics.py:90-109). */
+#define MDIMG_METRIC_COLS 24
+#define MDIMG_MC_MEAN 16
+#define MDIMG_MC_EDGE_RATIO 17
+#define MDIMG_MC_NIQE 18
+#define MDIMG_MC_VAR_OF_VAR 19
+#define MDIMG_MC_GMAX 20
+#define MDIMG_MC_P05 21
+#define MDIMG_MC_P95 22
+
+/* op codes for mdimg_workspace_bytes */
+enum mdimg_op {
+    MDIMG_OP_NORMALIZE = 1,
+    MDIMG_OP_METRICS = 2,
+    MDIMG_OP_SIGMA = 3,
+    MDIMG_OP_QUALITY = 4,
+    MDIMG_OP_FULLREF = 5,
+    MDIMG_OP_WAVELET = 6,
+    MDIMG_OP_CLAHE = 7,      /* param = kernel_size */
+    MDIMG_OP_GAMMA = 8,
+    MDIMG_OP_UNSHARP = 9,
+    MDIMG_OP_LIGHT_DENOISE = 10,
+    MDIMG_OP_BILATERAL = 11,
+    MDIMG_OP_TV = 12,        /* param = max_iter */
+    MDIMG_OP_MINMAX = 13
+};
+
+const char* mdimg_last_error(void);
+int mdimg_version(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+unsigned long long mdimg_launch_count(void);
+
+/* Select the device and verify it is compute capability 10.x (B200). */
+int mdimg_init(int device);
+int mdimg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes,
+                      size_t* total_mem);
+
+/* Device workspace needed by `op` for a stack of n slices of h x w (sized for n_sel == n). */
+size_t mdimg_workspace_bytes(int op, int n, int h, int w, int param);
+
+/* ---- ingestion ------------------------------------------------------------------------- */
+/* out_minmax: device float[n][2]. */
+int mdimg_minmax_f32(const float* img, int n, int h, int w, const int32_t* sel, int n_sel,
+                     float* out_minmax, void* ws, size_t ws_bytes, void* stream);
+/* normalize_image (pipeline/dicom_io.py:84-91): per-slice (x - min) / (max - min), zeros when
+ * max - min < 1e-8. */
+int mdimg_normalize_u16(const uint16_t* in, float* out, int n, int h, int w, const int32_t* sel,
+                        int n_sel, void* ws, size_t ws_bytes, void* stream);
+int mdimg_normalize_f32(const float* in, float* out, int n, int h, int w, const int32_t* sel,
+                        int n_sel, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- metrics ----------------------------------------------------------------------------- */
+/* compute_metrics (pipeline/metrics.py:42-109) for every slice; flags bit0 additionally fills
+ * MDIMG_MC_NIQE / MDIMG_MC_VAR_OF_VAR (compute_niqe_approximation, metrics.py:187-210).
+ * MDIMG_MC_EDGE_RATIO (compute_edge_ratio, metrics.py:213-217) is always filled.
+ * pct_lo / pct_hi / pct_gamma: HOST arrays of 5 entries — numpy's 'linear' percentile plan
+ * (previous index, next index, float32 weight) for q = 5, 25, 75, 95 (of the image) and 90 (of the
+ * gradient magnitude) at h*w elements.  out: device double[n][MDIMG_METRIC_COLS]. */
+int mdimg_metrics(const float* img, int n, int h, int w, const int32_t* sel, int n_sel, int flags,
+                  const int32_t* pct_lo, const int32_t* pct_hi, const float* pct_gamma,
+                  double* out, void* ws, size_t ws_bytes, void* stream);
+/* skimage.restoration.estimate_sigma(image, channel_axis=None, average_sigmas=True)
+ * (called at pipeline/metrics.py:47, pipeline/enhancement.py:59-60,82). sigma: device double[n]. */
+int mdimg_estimate_sigma(const float* img, int n, int h, int w, const int32_t* sel, int n_sel,
+                         double* sigma, void* ws, size_t ws_bytes, void* stream);
+/* out: device double[n][2] = (compute_edge_ratio, compute_niqe_approximation); flags bit0 enables
+ * the NIQE column (pipeline/metrics.py:187-217; guards at pipeline/enhancement.py:50-72). */
+int mdimg_quality(const float* img, int n, int h, int w, const int32_t* sel, int n_sel, int flags,
+                  double* out, void* ws, size_t ws_bytes, void* stream);
+/* skimage.metrics.structural_similarity / peak_signal_noise_ratio with data_range=1.0
+ * (pipeline/metrics.py:232-233). out: device double[n][2] = (ssim, psnr). */
+int mdimg_fullref(const float* original, const float* enhanced, int n, int h, int w,
+                  const int32_t* sel, int n_sel, double* out, void* ws, size_t ws_bytes,
+                  void* stream);
+
+/* ---- enhancement steps ------------------------------------------------------------------ */
+/* denoise_wavelet(image, channel_axis=None, rescale_sigma=True, mode=...[, sigma=...])
+ * (pipeline/enhancement.py:86,169,270,328).  sigma_in: device double[n] or NULL (estimate);
+ * the sigma used is sigma_in[s] * sigma_scale.  skip: device int32[n] or NULL. */
+int mdimg_wavelet_denoise(const float* in, float* out, int n, int h, int w, const int32_t* sel,
+                          int n_sel, int mode_hard, const double* sigma_in, double sigma_scale,
+                          const int32_t* skip, void* ws, size_t ws_bytes, void* stream);
+/* exposure.equalize_adapthist(image, clip_limit, kernel_size) (pipeline/enhancement.py:183,277,332).
+ * status: device int32[n]; 1 where the slice leaves [-1, 1] (the reference raises ValueError). */
+int mdimg_clahe(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                double clip_limit, int kernel_size, int32_t* status, void* ws, size_t ws_bytes,
+                void* stream);
+/* exposure.adjust_gamma(image, gamma) (pipeline/enhancement.py:194,197,284,336).
+ * neg_flag: device int32[n]; 1 where a slice holds a negative pixel (ValueError in the reference).
+ * assume_nonneg != 0 skips the min/max pre-pass (caller guarantees non-negative input). */
+int mdimg_gamma(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                double gamma, int assume_nonneg, int32_t* neg_flag, void* ws, size_t ws_bytes,
+                void* stream);
+/* filters.unsharp_mask(image, radius, amount) (pipeline/enhancement.py:202,290,338).
+ * weights: HOST double[gauss_radius + 1], scipy's normalised Gaussian taps w[0..R]. */
+int mdimg_unsharp(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                  const double* weights, int gauss_radius, double amount, int assume_nonneg,
+                  void* ws, size_t ws_bytes, void* stream);
+/* _light_denoise(image, strength) (pipeline/enhancement.py:80-94). skipped: device int32[n] or
+ * NULL, set to 1 where sigma < 0.001 returned the slice unchanged. */
+int mdimg_light_denoise(const float* in, float* out, int n, int h, int w, const int32_t* sel,
+                        int n_sel, double strength, int32_t* skipped, void* ws, size_t ws_bytes,
+                        void* stream);
+/* _bilateral_filter (pipeline/enhancement.py:102-143). d: odd effective diameter (1..9);
+ * spatial: HOST double[d*d] spatial weights. */
+int mdimg_bilateral(const float* in, float* out, int n, int h, int w, const int32_t* sel,
+                    int n_sel, int d, const double* spatial, double sigma_color, void* stream);
+/* denoise_tv_chambolle(image, weight, channel_axis=None) (pipeline/enhancement.py:311,349).
+ * iters: device int32[n] or NULL.  Synchronises `stream` every few iterations. */
+int mdimg_tv_chambolle(const float* in, float* out, int n, int h, int w, const int32_t* sel,
+                       int n_sel, double weight, double eps, int max_iter, int32_t* iters,
+                       void* ws, size_t ws_bytes, void* stream);
+/* out = c0*a + c1*b in float32 (optionally clipped to [0,1]): the blends at
+ * pipeline/enhancement.py:93,365. */
+int mdimg_axpby(const float* a, const float* b, float* out, int n, int h, int w, const int32_t* sel,
+                int n_sel, double c0, double c1, int clip01, void* stream);
+/* np.clip(x, 0, 1) (pipeline/enhancement.py:218,225,314,352,360,367). */
+int mdimg_clip01(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                 void* stream);
+int mdimg_copy(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDIMG_B200_H */

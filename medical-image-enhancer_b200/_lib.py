@@ -1,0 +1,116 @@
+"""ctypes binding of libmdimg_b200.so (C ABI declared in ``include/mdimg_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 device is present,
+the first compute call raises.  Loading the library itself needs no GPU (symbol checks run on
+the CPU-only build box).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from pathlib import Path
+
+LIB_NAME = "libmdimg_b200.so"
+LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
+
+MDIMG_OK = 0
+ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE = 1, 2, 3, 4
+METRIC_COLS = 24
+
+OP_NORMALIZE, OP_METRICS, OP_SIGMA, OP_QUALITY, OP_FULLREF, OP_WAVELET, OP_CLAHE, OP_GAMMA, \
+    OP_UNSHARP, OP_LIGHT_DENOISE, OP_BILATERAL, OP_TV, OP_MINMAX = range(1, 14)
+
+_p = C.c_void_p
+_i = C.c_int
+_d = C.c_double
+_sz = C.c_size_t
+
+# name -> (restype, argtypes).  Kept in one table so the CPU test-suite can check that every
+# symbol declared in include/mdimg_b200.h is exported.
+_IMG = [_i, _i, _i, _p, _i]          # n, h, w, sel, n_sel
+_WS = [_p, _sz, _p]                  # ws, ws_bytes, stream
+PROTOTYPES = {
+    "mdimg_last_error": (C.c_char_p, []),
+    "mdimg_version": (_i, []),
+    "mdimg_launch_count": (C.c_ulonglong, []),
+    "mdimg_init": (_i, [_i]),
+    "mdimg_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
+    "mdimg_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "mdimg_minmax_f32": (_i, [_p, *_IMG, _p, *_WS]),
+    "mdimg_normalize_u16": (_i, [_p, _p, *_IMG, *_WS]),
+    "mdimg_normalize_f32": (_i, [_p, _p, *_IMG, *_WS]),
+    "mdimg_metrics": (_i, [_p, *_IMG, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                           C.POINTER(C.c_float), _p, *_WS]),
+    "mdimg_estimate_sigma": (_i, [_p, *_IMG, _p, *_WS]),
+    "mdimg_quality": (_i, [_p, *_IMG, _i, _p, *_WS]),
+    "mdimg_fullref": (_i, [_p, _p, *_IMG, _p, *_WS]),
+    "mdimg_wavelet_denoise": (_i, [_p, _p, *_IMG, _i, _p, _d, _p, *_WS]),
+    "mdimg_clahe": (_i, [_p, _p, *_IMG, _d, _i, _p, *_WS]),
+    "mdimg_gamma": (_i, [_p, _p, *_IMG, _d, _i, _p, *_WS]),
+    "mdimg_unsharp": (_i, [_p, _p, *_IMG, C.POINTER(_d), _i, _d, _i, *_WS]),
+    "mdimg_light_denoise": (_i, [_p, _p, *_IMG, _d, _p, *_WS]),
+    "mdimg_bilateral": (_i, [_p, _p, *_IMG, _i, C.POINTER(_d), _d, _p]),
+    "mdimg_tv_chambolle": (_i, [_p, _p, *_IMG, _d, _d, _i, _p, *_WS]),
+    "mdimg_axpby": (_i, [_p, _p, _p, *_IMG, _d, _d, _i, _p]),
+    "mdimg_clip01": (_i, [_p, _p, *_IMG, _p]),
+    "mdimg_copy": (_i, [_p, _p, *_IMG, _p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+_initialised_devices: set[int] = set()
+
+
+class MdimgError(RuntimeError):
+    """Raised when a C-ABI call returns a non-zero status."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+def load_library() -> C.CDLL:
+    """dlopen libmdimg_b200.so and attach prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
+                "mdimg_b200 has no CPU fallback."
+            )
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)       # AttributeError here means the ABI and the binding drifted
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    msg = load_library().mdimg_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int) -> None:
+    if rc == MDIMG_OK:
+        return
+    msg = last_error()
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    raise MdimgError(rc, msg or f"mdimg_b200 call failed with status {rc}")
+
+
+def ensure_device(index: int) -> None:
+    """mdimg_init once per device; raises (no fallback) when the device is not an sm_100 GPU."""
+    if index in _initialised_devices:
+        return
+    lib = load_library()
+    check(lib.mdimg_init(int(index)))
+    _initialised_devices.add(index)

@@ -1,0 +1,98 @@
+// Bilateral filter: the reference's own numpy implementation, pipeline/enhancement.py:102-143.
+//
+//   padded = np.pad(image, r, 'reflect')                      whole-sample mirror
+//   for dy, dx (dy-major):  diff = image - shifted            float32
+//       iw = exp(-(diff**2) / (2*sc**2))                      float32 (python-float divisor)
+//       w  = spatial[dy, dx] * iw                             float64 (np.float64 scalar * float32)
+//       result += w * shifted ; weight_sum += w               float64 add, stored back as float32
+//   out = result / (weight_sum + 1e-10)                       float32
+//
+// One shared-memory tile with a (d//2)-pixel halo per CTA; the slice is read once and written
+// once.  d*d exponentials per pixel make this kernel MUFU/FP64-issue bound rather than HBM bound
+// for d >= 5 (stated in DESIGN.md).
+#include "enhance.cuh"
+
+namespace mdimg {
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int TW = 64, TH = 32;
+constexpr int MAXD = 9;
+
+struct SpatialW { double w[MAXD * MAXD]; };
+
+template <int R>
+__global__ void __launch_bounds__(NT)
+k_bilateral(const float* __restrict__ in, float* __restrict__ out, Dims d, const SpatialW sw,
+            float two_sc2) {
+    constexpr int D = 2 * R + 1;
+    constexpr int XW = TW + 2 * R, XH = TH + 2 * R, XP = XW + 1;
+    __shared__ float X[XH][XP];
+    const int s = slice_of(d.sel, blockIdx.y);
+    const int tiles_x = (d.w + TW - 1) / TW;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const float* src = in + (size_t)s * d.h * d.w;
+    float* dst = out + (size_t)s * d.h * d.w;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < XH * XW; i += NT) {
+        int r = i / XW, c = i - r * XW;
+        int gy = refl_mirror(y0 + r - R, d.h), gx = refl_mirror(x0 + c - R, d.w);
+        X[r][c] = src[(size_t)gy * d.w + gx];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j2 = 0; j2 < TH / 8; ++j2)
+#pragma unroll
+        for (int i2 = 0; i2 < TW / 32; ++i2) {
+            const int r = wid + 8 * j2, c = lane + 32 * i2;
+            const int gy = y0 + r, gx = x0 + c;
+            if (gy < d.h && gx < d.w) {
+                const float xc = X[r + R][c + R];
+                float res = 0.0f, wsum = 0.0f;
+#pragma unroll
+                for (int dy = 0; dy < D; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < D; ++dx) {
+                        const float nb = X[r + dy][c + dx];
+                        const float diff = __fsub_rn(xc, nb);
+                        const float arg = __fdiv_rn(-__fmul_rn(diff, diff), two_sc2);
+                        const float iw = expf(arg);
+                        const double w = __dmul_rn(sw.w[dy * D + dx], (double)iw);
+                        res = (float)__dadd_rn((double)res, __dmul_rn(w, (double)nb));
+                        wsum = (float)__dadd_rn((double)wsum, w);
+                    }
+                dst[(size_t)gy * d.w + gx] = __fdiv_rn(res, __fadd_rn(wsum, 1e-10f));
+            }
+        }
+}
+
+template <int R>
+void launch(const float* in, float* out, const Dims& d, const SpatialW& sw, float two_sc2, cudaStream_t st) {
+    dim3 grid(((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH), d.n_sel);
+    MDIMG_LAUNCH k_bilateral<R><<<grid, NT, 0, st>>>(in, out, d, sw, two_sc2);
+}
+
+}  // namespace
+
+int bilateral_run(const float* in, float* out, const Dims& d, int dd, const double* spatial,
+                  double sigma_color, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    if (dd < 1 || dd > MAXD || (dd & 1) == 0)
+        return set_error(MDIMG_ERR_INVALID, "bilateral: diameter %d must be odd and in [1, 9]", dd);
+    if (in == out) return set_error(MDIMG_ERR_INVALID, "bilateral: in-place operation is not supported");
+    SpatialW sw;
+    for (int i = 0; i < MAXD * MAXD; ++i) sw.w[i] = i < dd * dd ? spatial[i] : 0.0;
+    const float two_sc2 = (float)(2.0 * sigma_color * sigma_color);
+    switch (dd / 2) {
+        case 0: launch<0>(in, out, d, sw, two_sc2, stream); break;
+        case 1: launch<1>(in, out, d, sw, two_sc2, stream); break;
+        case 2: launch<2>(in, out, d, sw, two_sc2, stream); break;
+        case 3: launch<3>(in, out, d, sw, two_sc2, stream); break;
+        case 4: launch<4>(in, out, d, sw, two_sc2, stream); break;
+    }
+    return check_launch("bilateral");
+}
+
+}  // namespace mdimg

@@ -1,0 +1,302 @@
+// CLAHE: skimage.exposure.equalize_adapthist(image, clip_limit, kernel_size) as called at
+// pipeline/enhancement.py:183,277,332 (skimage/exposure/_adapthist.py, NR_OF_GRAY = 16384,
+// nbins = 256).  Integer / indexing work, reproduced bit-exactly:
+//
+//   u   = uint16(clip(rint(float32(x) * 65535), 0, 65535))                 img_as_uint
+//   q   = uint16(rint_half_even((u - umin) / (umax - umin) * 16383))       float64 rescale
+//   pad = np.pad(q, (k//2, (k - s%k)%k + ceil(k/2)), 'reflect')            whole-sample mirror
+//   b   = q // 65                                                           256 gray bins (0..252)
+//   per k x k contextual region: bincount -> clip_histogram (sequential redistribute loop)
+//        -> map = int(min(cumsum * (16383 / k^2), 16383))
+//   per pixel: float32 accumulation, in corner order (0,0),(0,1),(1,0),(1,1), of
+//        float32(float64(map[b]) * (wx * wy)); truncate to uint16
+//   out = (v - vmin) / (vmax - vmin) in float32                            final rescale_intensity
+//
+// Kernels: k_clahe_hist (one warp per contextual region: quantise, histogram in shared memory,
+// clip/redistribute, CDF -> uint16 LUT; also stores the 8-bit bin image), k_clahe_blend (bilinear
+// LUT blend -> uint16 + per-slice min/max), k_clahe_final (float32 stretch).
+#include "enhance.cuh"
+
+namespace mdimg {
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int WARPS = NT / 32;
+constexpr int NBINS = 256;
+
+struct ClaheGeom {
+    int k;          // kernel_size (same on both axes)
+    int nty, ntx;   // contextual regions per axis
+    int clim;
+    double scale;   // 16383 / k^2
+};
+
+struct SliceRange {   // per slice: umin, umax of the uint16 image; vmin/vmax of the blended image
+    unsigned umin, umax;
+    unsigned vmin, vmax;
+};
+
+__device__ __forceinline__ unsigned to_u16(float x) {
+    float t = rintf(__fmul_rn(x, 65535.0f));
+    t = fminf(fmaxf(t, 0.0f), 65535.0f);
+    return (unsigned)t;
+}
+
+__global__ void k_clahe_prep(Dims d, const uint2* __restrict__ mm, SliceRange* __restrict__ rng,
+                             int* __restrict__ status) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= d.n_sel) return;
+    int s = slice_of(d.sel, si);
+    float mn = key2f(mm[s].x), mx = key2f(mm[s].y);
+    status[s] = (mn < -1.0f || mx > 1.0f) ? 1 : 0;
+    SliceRange r;
+    r.umin = to_u16(mn);          // rint(x*65535) is monotone, so min/max commute with it
+    r.umax = to_u16(mx);
+    r.vmin = 0xFFFFFFFFu;
+    r.vmax = 0u;
+    rng[si] = r;
+}
+
+__device__ __forceinline__ unsigned quantise(float x, unsigned umin, unsigned umax) {
+    unsigned u = to_u16(x);
+    if (umin == umax) return u > 16383u ? 16383u : u;
+    double t = __ddiv_rn((double)(int)(u - umin), (double)(int)(umax - umin));
+    t = __dadd_rn(__dmul_rn(t, 16383.0), 0.0);
+    return (unsigned)rint(t);
+}
+
+// One warp per contextual region.
+__global__ void __launch_bounds__(NT)
+k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const SliceRange* __restrict__ rng,
+             const int* __restrict__ status, uint8_t* __restrict__ bins, uint16_t* __restrict__ maps) {
+    __shared__ int hist[WARPS][NBINS];
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    if (status[s]) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tile = blockIdx.x * WARPS + wid;
+    if (tile >= g.nty * g.ntx) return;
+    const int ty = tile / g.ntx, tx = tile - ty * g.ntx;
+    const int k = g.k;
+    const unsigned umin = rng[si].umin, umax = rng[si].umax;
+    int* h = hist[wid];
+    for (int i = lane; i < NBINS; i += 32) h[i] = 0;
+    __syncwarp();
+    const float* src = in + (size_t)s * d.h * d.w;
+    uint8_t* bdst = bins + (size_t)si * d.h * d.w;
+    const int kk = k * k;
+    for (int i = lane; i < kk; i += 32) {
+        const int ry = i / k, rx = i - ry * k;
+        const int oy = ty * k + ry, ox = tx * k + rx;        // padded index minus pad_start
+        const int gy = refl_mirror(oy, d.h), gx = refl_mirror(ox, d.w);
+        const unsigned q = quantise(src[(size_t)gy * d.w + gx], umin, umax);
+        const int b = (int)(q / 65u);
+        atomicAdd(&h[b], 1);
+        if (oy < d.h && ox < d.w) bdst[(size_t)oy * d.w + ox] = (uint8_t)b;
+    }
+    __syncwarp();
+
+    // ---- clip_histogram, bins j = lane + 32*m held in registers ----
+    int hv[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) hv[m] = h[lane + 32 * m];
+    const int clim = g.clim;
+    int part = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        if (hv[m] > clim) { part += hv[m] - clim; hv[m] = clim; }
+    }
+    int n_excess = __reduce_add_sync(0xffffffffu, part);
+    const int bin_incr = n_excess / NBINS;
+    const int upper = clim - bin_incr;
+    part = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        if (hv[m] < upper) { hv[m] += bin_incr; part += 1; }
+    }
+    n_excess -= __reduce_add_sync(0xffffffffu, part) * bin_incr;
+    part = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        if (hv[m] >= upper && hv[m] < clim) { part += hv[m] - clim; hv[m] = clim; }
+    }
+    n_excess += __reduce_add_sync(0xffffffffu, part);
+
+    while (n_excess > 0) {
+        const int prev = n_excess;
+        for (int index = 0; index < NBINS; ++index) {
+            int under = 0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) under += (hv[m] < clim);
+            under = __reduce_add_sync(0xffffffffu, under);
+            int step = under / n_excess;
+            if (step < 1) step = 1;
+            int cnt = 0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int j = lane + 32 * m;
+                if (j >= index && ((j - index) % step) == 0 && hv[m] < clim) { hv[m] += 1; cnt += 1; }
+            }
+            n_excess -= __reduce_add_sync(0xffffffffu, cnt);
+            if (n_excess <= 0) break;
+        }
+        if (prev == n_excess) break;
+    }
+
+    // ---- map_histogram: cumulative sum in bin order, scaled in float64, truncated ----
+    uint16_t* mdst = maps + ((size_t)si * g.nty * g.ntx + tile) * NBINS;
+    int carry = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        int inc = hv[m];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int cum = carry + inc;
+        double v = __dadd_rn(__dmul_rn((double)cum, g.scale), 0.0);
+        if (v > 16383.0) v = 16383.0;
+        mdst[lane + 32 * m] = (uint16_t)(int)v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+constexpr int BW = 64, BH = 4;   // blend tile: 256 threads, one pixel each, rows of 64
+
+__global__ void __launch_bounds__(NT)
+k_clahe_blend(Dims d, ClaheGeom g, SliceRange* __restrict__ rng, const int* __restrict__ status,
+              const uint8_t* __restrict__ bins, const uint16_t* __restrict__ maps,
+              uint16_t* __restrict__ vout) {
+    __shared__ double coef[48], icoef[48];
+    __shared__ unsigned smin[WARPS], smax[WARPS];
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    if (status[s]) return;
+    const int k = g.k;
+    if (threadIdx.x < k) {
+        double c = __ddiv_rn((double)threadIdx.x, (double)k);   // np.arange(k) / k
+        coef[threadIdx.x] = c;
+        icoef[threadIdx.x] = __dsub_rn(1.0, c);
+    }
+    __syncthreads();
+    const int tiles_x = (d.w + BW - 1) / BW;
+    const int bx = blockIdx.x % tiles_x, by = blockIdx.x / tiles_x;
+    const int x = bx * BW + (threadIdx.x & (BW - 1));
+    const int y = by * BH + (threadIdx.x / BW);
+    unsigned vmin = 0xFFFFFFFFu, vmax = 0u;
+    if (x < d.w && y < d.h) {
+        const size_t o = (size_t)y * d.w + x;
+        const int b = bins[(size_t)si * d.h * d.w + o];
+        const int py = y + k / 2, px = x + k / 2;
+        const int byk = py / k, iy = py - byk * k;
+        const int bxk = px / k, ix = px - bxk * k;
+        // map_array is the LUT grid edge-padded by one: entry j -> region clamp(j - 1)
+        const int t0y = min(max(byk - 1, 0), g.nty - 1), t1y = min(byk, g.nty - 1);
+        const int t0x = min(max(bxk - 1, 0), g.ntx - 1), t1x = min(bxk, g.ntx - 1);
+        const uint16_t* mbase = maps + (size_t)si * g.nty * g.ntx * NBINS;
+        const double wy0 = icoef[iy], wy1 = coef[iy], wx0 = icoef[ix], wx1 = coef[ix];
+        float acc = 0.0f;
+        acc = __fadd_rn(acc, (float)__dmul_rn((double)mbase[((size_t)t0y * g.ntx + t0x) * NBINS + b], __dmul_rn(wx0, wy0)));
+        acc = __fadd_rn(acc, (float)__dmul_rn((double)mbase[((size_t)t0y * g.ntx + t1x) * NBINS + b], __dmul_rn(wx1, wy0)));
+        acc = __fadd_rn(acc, (float)__dmul_rn((double)mbase[((size_t)t1y * g.ntx + t0x) * NBINS + b], __dmul_rn(wx0, wy1)));
+        acc = __fadd_rn(acc, (float)__dmul_rn((double)mbase[((size_t)t1y * g.ntx + t1x) * NBINS + b], __dmul_rn(wx1, wy1)));
+        const unsigned v = (unsigned)acc;      // astype(uint16): truncation
+        vout[(size_t)si * d.h * d.w + o] = (uint16_t)v;
+        vmin = v; vmax = v;
+    }
+    vmin = __reduce_min_sync(0xffffffffu, vmin);
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { smin[wid] = vmin; smax[wid] = vmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < WARPS; ++w) { vmin = min(vmin, smin[w]); vmax = max(vmax, smax[w]); }
+        atomicMin(&rng[si].vmin, vmin);
+        atomicMax(&rng[si].vmax, vmax);
+    }
+}
+
+__global__ void __launch_bounds__(NT)
+k_clahe_final(Dims d, const SliceRange* __restrict__ rng, const int* __restrict__ status,
+              const uint16_t* __restrict__ vin, float* __restrict__ out) {
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    if (status[s]) return;
+    const long long len = d.px();
+    const uint16_t* v = vin + (size_t)si * len;
+    float* o = out + (size_t)s * len;
+    const unsigned vmin = rng[si].vmin, vmax = rng[si].vmax;
+    const float lo = (float)vmin;
+    const float den = (float)((double)vmax - (double)vmin);
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < len; i += (long long)gridDim.x * NT) {
+        const float f = (float)v[i];
+        float r;
+        if (vmin != vmax) r = __fdiv_rn(__fsub_rn(f, lo), den);
+        else r = fminf(fmaxf(f, 0.0f), 1.0f);
+        o[i] = r;
+    }
+}
+
+struct ClaheBufs { SliceRange* rng; uint8_t* bins; uint16_t* maps; uint16_t* v; };
+
+void carve(Arena& a, int n_sel, int h, int w, int nty, int ntx, ClaheBufs& b) {
+    b.rng = a.take<SliceRange>(n_sel);
+    b.bins = a.take<uint8_t>((size_t)n_sel * h * w);
+    b.maps = a.take<uint16_t>((size_t)n_sel * nty * ntx * NBINS);
+    b.v = a.take<uint16_t>((size_t)n_sel * h * w);
+}
+
+inline void geom(int h, int w, int k, double clip_limit, ClaheGeom& g) {
+    g.k = k;
+    g.nty = (h + k - 1) / k;      // int(padded / k) - 1 with padded = ceil(s/k)*k + k
+    g.ntx = (w + k - 1) / k;
+    const int kk = k * k;
+    if (clip_limit > 0.0) {
+        double c = clip_limit * (double)kk;
+        if (c < 1.0) c = 1.0;
+        g.clim = (int)c;
+    } else {
+        g.clim = 65535;           // np.iinfo(uint16).max: no clipping (AHE)
+    }
+    g.scale = 16383.0 / (double)kk;
+}
+
+}  // namespace
+
+size_t clahe_workspace_bytes(int n, int n_sel, int h, int w, int kernel_size) {
+    (void)n;
+    if (kernel_size < 1) return 0;
+    Arena a(nullptr, 0);
+    ClaheBufs b;
+    ClaheGeom g;
+    geom(h, w, kernel_size, 0.01, g);
+    carve(a, n_sel, h, w, g.nty, g.ntx, b);
+    return a.off;
+}
+
+int clahe_run(const float* in, float* out, const Dims& d, double clip_limit, int kernel_size,
+              const uint2* mm, int* status, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    if (kernel_size < 1 || kernel_size > 48)
+        return set_error(MDIMG_ERR_INVALID, "clahe: kernel_size %d outside [1, 48]", kernel_size);
+    ClaheGeom g;
+    geom(d.h, d.w, kernel_size, clip_limit, g);
+    Arena a(ws, ws_bytes);
+    ClaheBufs b;
+    carve(a, d.n_sel, d.h, d.w, g.nty, g.ntx, b);
+    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "clahe: workspace too small (%zu > %zu)", a.off, ws_bytes);
+    MDIMG_LAUNCH k_clahe_prep<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, mm, b.rng, status);
+    const int ntiles = g.nty * g.ntx;
+    MDIMG_LAUNCH k_clahe_hist<<<dim3((ntiles + WARPS - 1) / WARPS, d.n_sel), NT, 0, stream>>>(in, d, g, b.rng, status, b.bins, b.maps);
+    dim3 bgrid(((d.w + BW - 1) / BW) * ((d.h + BH - 1) / BH), d.n_sel);
+    MDIMG_LAUNCH k_clahe_blend<<<bgrid, NT, 0, stream>>>(d, g, b.rng, status, b.bins, b.maps, b.v);
+    long long len = d.px();
+    int fb = (int)((len + NT * 8 - 1) / (NT * 8));
+    if (fb > 4096) fb = 4096;
+    MDIMG_LAUNCH k_clahe_final<<<dim3(fb, d.n_sel), NT, 0, stream>>>(d, b.rng, status, b.v, out);
+    return check_launch("clahe");
+}
+
+}  // namespace mdimg

@@ -1,0 +1,683 @@
+// Quality metrics on device: the 16 no-reference metrics of the reference's compute_metrics
+// (pipeline/metrics.py:42-109), estimate_sigma (skimage, called at metrics.py:47), the edge ratio
+// (metrics.py:213-217) and the NIQE approximation (metrics.py:187-210).
+//
+// Data flow for one batch of slices (all per-slice scalars stay on the device):
+//   k_stencil_stats : one read of the image -> Laplacian / Sobel / 7x7 box statistics, 256-bin
+//                     histogram, level-1 radix histograms of x and |grad|, max|grad|; writes |grad|
+//   k_db2_dd        : 1-level db2 'dd' band (float32 accumulation order of pywt) -> |dd|, zero count
+//   select_run x3   : exact order statistics (P5/P25/P75/P95 of x, P90 of |grad|, median |dd|)
+//   k_grad_prep/k_grad_pass : the three |grad| statistics that depend on max / P90 of |grad|
+//   k_finalize      : the 16 numbers (+ mean, edge ratio, NIQE) per slice
+#include "metrics.cuh"
+
+namespace mdimg {
+
+namespace {
+
+constexpr int TW = 64, TH = 32, HALO = 3;
+constexpr int XW = TW + 2 * HALO;   // 70
+constexpr int XH = TH + 2 * HALO;   // 38
+constexpr int XP = XW + 1;          // smem pitch
+constexpr int NT = 256;
+
+struct MetAcc {               // per slice, zero-initialised
+    double sum_x, sum_x2, sum_lap, sum_lap2, sum_abslap, sum_g, sum_g2, sum_ls, sum_ls2;
+    double sum_strong;
+    double box16[2];          // sum lv, sum lv^2 (NIQE)
+    unsigned long long cnt_low, cnt_high, cnt_lt0, cnt_gt1, cnt_edge, cnt_strong;
+    unsigned gmax_key;
+    unsigned dd_zero;         // number of exactly-zero 'dd' coefficients
+    unsigned hist256[256];
+    unsigned hist128[128];
+};
+
+struct GradPrep {             // per slice, derived from max|grad| and P90
+    float edges[129];
+    float denom;              // float32(last_edge)
+    float last;               // float32(last_edge) for the keep test
+    float thr_edge;           // 0.1f * gmax
+    float t90;                // np.percentile(grad, 90)
+};
+
+__device__ __forceinline__ float lerp_np(float a, float b, float t) {
+    // numpy _lerp in float32: a + (b-a)*t, or b - (b-a)*(1-t) when t >= 0.5
+    float diff = __fsub_rn(b, a);
+    float r = __fadd_rn(a, __fmul_rn(diff, t));
+    if (t >= 0.5f) r = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, t)));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused stencil statistics (one read of the image).
+// ---------------------------------------------------------------------------------------
+struct StencilSmem {
+    float X[XH][XP];
+    float VS[TH][XP];
+    float VQ[TH][XP];
+    unsigned h256[256];
+    unsigned hx[SEL_L1_BINS];
+    unsigned hg[SEL_L1_BINS];
+    double red[9 * 32];
+};
+
+__global__ void __launch_bounds__(NT)
+k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
+                float* __restrict__ gout, unsigned* __restrict__ l1x, unsigned* __restrict__ l1g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StencilSmem& sm = *reinterpret_cast<StencilSmem*>(smem_raw);
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    const int tiles_x = (d.w + TW - 1) / TW;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const float* src = img + (size_t)s * d.h * d.w;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    for (int i = tid; i < 256; i += NT) sm.h256[i] = 0;
+    for (int i = tid; i < SEL_L1_BINS; i += NT) { sm.hx[i] = 0; sm.hg[i] = 0; }
+
+    // tile + halo, half-sample symmetric border (scipy.ndimage mode='reflect')
+    for (int i = tid; i < XH * XW; i += NT) {
+        int r = i / XW, c = i - r * XW;
+        int gy = refl_sym(y0 + r - HALO, d.h);
+        int gx = refl_sym(x0 + c - HALO, d.w);
+        sm.X[r][c] = src[(size_t)gy * d.w + gx];
+    }
+    __syncthreads();
+
+    // axis-0 pass of uniform_filter(size=7) on x and x*x: double sum, /7, round to float32
+    const double inv7 = 1.0 / 7.0;
+    for (int i = tid; i < TH * XW; i += NT) {
+        int r = i / XW, c = i - r * XW;
+        double a = 0.0, q = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            float v = sm.X[r + k][c];
+            a += (double)v;
+            q += (double)__fmul_rn(v, v);
+        }
+        sm.VS[r][c] = (float)(a * inv7);
+        sm.VQ[r][c] = (float)(q * inv7);
+    }
+    __syncthreads();
+
+    double acc_v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned c_low = 0, c_high = 0, c_lt0 = 0, c_gt1 = 0;
+    float gmax = 0.0f;
+    float* gdst = gout + (size_t)s * d.h * d.w;
+
+#pragma unroll
+    for (int j = 0; j < TH / 8; ++j) {
+#pragma unroll
+        for (int i = 0; i < TW / 32; ++i) {
+            const int r = wid + 8 * j, c = lane + 32 * i;
+            const int gy = y0 + r, gx = x0 + c;
+            if (gy < d.h && gx < d.w) {
+                const int rr = r + HALO, cc = c + HALO;
+                const float xc = sm.X[rr][cc];
+                const double n00 = sm.X[rr - 1][cc - 1], n01 = sm.X[rr - 1][cc], n02 = sm.X[rr - 1][cc + 1];
+                const double n10 = sm.X[rr][cc - 1], n12 = sm.X[rr][cc + 1];
+                const double n20 = sm.X[rr + 1][cc - 1], n21 = sm.X[rr + 1][cc], n22 = sm.X[rr + 1][cc + 1];
+                // scipy.ndimage.convolve accumulates in double and stores float32
+                const float lap = (float)(4.0 * (double)xc - n01 - n10 - n12 - n21);
+                const float sh = (float)(0.25 * (n00 - n20) + 0.5 * (n01 - n21) + 0.25 * (n02 - n22));
+                const float sv = (float)(0.25 * (n00 - n02) + 0.5 * (n10 - n12) + 0.25 * (n20 - n22));
+                const float g = __fsqrt_rn(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
+                gdst[(size_t)gy * d.w + gx] = g;
+                gmax = fmaxf(gmax, g);
+
+                // axis-1 pass of the 7x7 box means
+                double ms = 0.0, mq = 0.0;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) { ms += (double)sm.VS[r][c + k]; mq += (double)sm.VQ[r][c + k]; }
+                const float m = (float)(ms * inv7), q = (float)(mq * inv7);
+                const float lv = fmaxf(__fsub_rn(q, __fmul_rn(m, m)), 0.0f);
+                const float ls = __fsqrt_rn(lv);
+
+                acc_v[0] += (double)xc;
+                acc_v[1] += (double)xc * (double)xc;
+                acc_v[2] += (double)lap;
+                acc_v[3] += (double)__fmul_rn(lap, lap);
+                acc_v[4] += (double)fabsf(lap);
+                acc_v[5] += (double)g;
+                acc_v[6] += (double)g * (double)g;
+                acc_v[7] += (double)ls;
+                acc_v[8] += (double)ls * (double)ls;
+                c_low += (xc <= 0.01f);
+                c_high += (xc >= 0.99f);
+                c_lt0 += (xc < 0.0f);
+                c_gt1 += (xc > 1.0f);
+
+                // np.histogram(bins=256, range=(0,1)): exact power-of-two edges
+                if (xc >= 0.0f && xc <= 1.0f) {
+                    int b = (int)(xc * 256.0f);
+                    if (b > 255) b = 255;
+                    atomicAdd(&sm.h256[b], 1u);
+                }
+                atomicAdd(&sm.hx[f2key(xc) >> 21], 1u);
+                atomicAdd(&sm.hg[f2key(g) >> 21], 1u);
+            }
+        }
+    }
+    __syncthreads();
+
+    block_sum<9>(acc_v, sm.red);
+    MetAcc* A = acc + si;
+    unsigned cl = warp_sum_u(c_low), ch = warp_sum_u(c_high), c0 = warp_sum_u(c_lt0), c1 = warp_sum_u(c_gt1);
+    float gm = warp_max(gmax);
+    if (lane == 0) {
+        if (cl) atomicAdd(&A->cnt_low, (unsigned long long)cl);
+        if (ch) atomicAdd(&A->cnt_high, (unsigned long long)ch);
+        if (c0) atomicAdd(&A->cnt_lt0, (unsigned long long)c0);
+        if (c1) atomicAdd(&A->cnt_gt1, (unsigned long long)c1);
+        atomicMax(&A->gmax_key, f2key(gm));
+    }
+    if (tid == 0) {
+        atomicAdd(&A->sum_x, acc_v[0]); atomicAdd(&A->sum_x2, acc_v[1]);
+        atomicAdd(&A->sum_lap, acc_v[2]); atomicAdd(&A->sum_lap2, acc_v[3]);
+        atomicAdd(&A->sum_abslap, acc_v[4]); atomicAdd(&A->sum_g, acc_v[5]);
+        atomicAdd(&A->sum_g2, acc_v[6]); atomicAdd(&A->sum_ls, acc_v[7]);
+        atomicAdd(&A->sum_ls2, acc_v[8]);
+    }
+    for (int i = tid; i < 256; i += NT) { unsigned v = sm.h256[i]; if (v) atomicAdd(&A->hist256[i], v); }
+    unsigned* gx_ = l1x + (size_t)si * SEL_L1_BINS;
+    unsigned* gg_ = l1g + (size_t)si * SEL_L1_BINS;
+    for (int i = tid; i < SEL_L1_BINS; i += NT) {
+        unsigned v = sm.hx[i]; if (v) atomicAdd(&gx_[i], v);
+        unsigned u = sm.hg[i]; if (u) atomicAdd(&gg_[i], u);
+    }
+}
+
+// Light variant for the halo guard / NIQE: only sum|laplace| and sum|grad|.
+constexpr int EW = 64, EH = 32, EXW = EW + 2, EXH = EH + 2, EXP = EXW + 1;
+
+__global__ void __launch_bounds__(NT)
+k_edge_stats(const float* __restrict__ img, Dims d, double* __restrict__ acc2) {
+    __shared__ float X[EXH][EXP];
+    __shared__ double red[2 * 32];
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    const int tiles_x = (d.w + EW - 1) / EW;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int x0 = tx * EW, y0 = ty * EH;
+    const float* src = img + (size_t)s * d.h * d.w;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < EXH * EXW; i += NT) {
+        int r = i / EXW, c = i - r * EXW;
+        int gy = refl_sym(y0 + r - 1, d.h), gx = refl_sym(x0 + c - 1, d.w);
+        X[r][c] = src[(size_t)gy * d.w + gx];
+    }
+    __syncthreads();
+    double v[2] = {0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < EH / 8; ++j)
+#pragma unroll
+        for (int i = 0; i < EW / 32; ++i) {
+            const int r = wid + 8 * j, c = lane + 32 * i;
+            if (y0 + r < d.h && x0 + c < d.w) {
+                const int rr = r + 1, cc = c + 1;
+                const double xc = X[rr][cc];
+                const double n00 = X[rr - 1][cc - 1], n01 = X[rr - 1][cc], n02 = X[rr - 1][cc + 1];
+                const double n10 = X[rr][cc - 1], n12 = X[rr][cc + 1];
+                const double n20 = X[rr + 1][cc - 1], n21 = X[rr + 1][cc], n22 = X[rr + 1][cc + 1];
+                const float lap = (float)(4.0 * xc - n01 - n10 - n12 - n21);
+                const float sh = (float)(0.25 * (n00 - n20) + 0.5 * (n01 - n21) + 0.25 * (n02 - n22));
+                const float sv = (float)(0.25 * (n00 - n02) + 0.5 * (n10 - n12) + 0.25 * (n20 - n22));
+                const float g = __fsqrt_rn(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
+                v[0] += (double)fabsf(lap);
+                v[1] += (double)g;
+            }
+        }
+    block_sum<2>(v, red);
+    if (tid == 0) {
+        atomicAdd(&acc2[(size_t)si * 2 + 0], v[0]);
+        atomicAdd(&acc2[(size_t)si * 2 + 1], v[1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// estimate_sigma: pywt.dwtn(x, 'db2')['dd'] with float32 accumulation, then |dd|.
+// ---------------------------------------------------------------------------------------
+constexpr int DT = 32;                  // dd outputs per tile edge
+constexpr int DIN = 2 * DT + 2;         // 66 input rows / cols
+constexpr int DP = DIN + 1;
+
+__global__ void __launch_bounds__(NT)
+k_db2_dd(const float* __restrict__ img, Dims d, int hd, int wd, float* __restrict__ absdd,
+         unsigned* __restrict__ l1, MetAcc* __restrict__ acc) {
+    __shared__ float IN[DIN][DP];
+    __shared__ float T[DT][DP];
+    __shared__ unsigned hh[SEL_L1_BINS];
+    const float f0 = (float)-0.48296291314453416, f1 = (float)0.8365163037378079,
+                f2 = (float)-0.2241438680420134, f3 = (float)-0.12940952255126037;
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    const int tiles_x = (wd + DT - 1) / DT;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int ox0 = tx * DT, oy0 = ty * DT;
+    const float* src = img + (size_t)s * d.h * d.w;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < SEL_L1_BINS; i += NT) hh[i] = 0;
+    for (int i = tid; i < DIN * DIN; i += NT) {
+        int r = i / DIN, c = i - r * DIN;
+        int gy = refl_sym(2 * oy0 - 2 + r, d.h), gx = refl_sym(2 * ox0 - 2 + c, d.w);
+        IN[r][c] = src[(size_t)gy * d.w + gx];
+    }
+    __syncthreads();
+    // axis 0: out[o] = ((f0*x[2o+1] + f1*x[2o]) + f2*x[2o-1]) + f3*x[2o-2]
+    for (int i = tid; i < DT * DIN; i += NT) {
+        int r = i / DIN, c = i - r * DIN;
+        float a = __fmul_rn(f0, IN[2 * r + 3][c]);
+        a = __fadd_rn(a, __fmul_rn(f1, IN[2 * r + 2][c]));
+        a = __fadd_rn(a, __fmul_rn(f2, IN[2 * r + 1][c]));
+        a = __fadd_rn(a, __fmul_rn(f3, IN[2 * r][c]));
+        T[r][c] = a;
+    }
+    __syncthreads();
+    unsigned nz = 0;
+    float* dst = absdd + (size_t)s * hd * wd;
+    for (int i = tid; i < DT * DT; i += NT) {
+        int r = i / DT, c = i - r * DT;
+        int oy = oy0 + r, ox = ox0 + c;
+        if (oy < hd && ox < wd) {
+            float a = __fmul_rn(f0, T[r][2 * c + 3]);
+            a = __fadd_rn(a, __fmul_rn(f1, T[r][2 * c + 2]));
+            a = __fadd_rn(a, __fmul_rn(f2, T[r][2 * c + 1]));
+            a = __fadd_rn(a, __fmul_rn(f3, T[r][2 * c]));
+            a = fabsf(a);
+            dst[(size_t)oy * wd + ox] = a;
+            nz += (a == 0.0f);
+            atomicAdd(&hh[f2key(a) >> 21], 1u);
+        }
+    }
+    __syncthreads();
+    nz = warp_sum_u(nz);
+    if (lane == 0 && nz) atomicAdd(&acc[si].dd_zero, nz);
+    unsigned* g = l1 + (size_t)si * SEL_L1_BINS;
+    for (int i = tid; i < SEL_L1_BINS; i += NT) { unsigned v = hh[i]; if (v) atomicAdd(&g[i], v); }
+}
+
+// ranks of the two middle non-zero |dd| values (np.median after dropping exact zeros)
+__global__ void k_sigma_ranks(Dims d, int len, const MetAcc* __restrict__ acc, int* __restrict__ ranks) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= d.n_sel) return;
+    int s = slice_of(d.sel, si);
+    int nz = (int)acc[si].dd_zero;
+    int m = len - nz;
+    if (m <= 0) { ranks[s * 2] = -1; ranks[s * 2 + 1] = -1; return; }
+    ranks[s * 2] = nz + (m - 1) / 2;
+    ranks[s * 2 + 1] = nz + m / 2;
+}
+
+__device__ __forceinline__ double sigma_from_pair(float a, float b) {
+    float med = __fdiv_rn(__fadd_rn(a, b), 2.0f);
+    return (double)med / 0.6744897501960817;
+}
+
+__global__ void k_sigma_out(Dims d, const float* __restrict__ sel_out, double* __restrict__ sigma) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= d.n_sel) return;
+    int s = slice_of(d.sel, si);
+    sigma[s] = sigma_from_pair(sel_out[s * 2], sel_out[s * 2 + 1]);
+}
+
+__global__ void k_fill_ranks(Dims d, int Q, const int* __restrict__ src, int* __restrict__ ranks) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_sel * Q) return;
+    int si = i / Q, q = i - si * Q;
+    int s = slice_of(d.sel, si);
+    ranks[s * Q + q] = src[q];
+}
+
+// ---------------------------------------------------------------------------------------
+// |grad| statistics that need max|grad| and P90(|grad|) first.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160)
+k_grad_prep(Dims d, const MetAcc* __restrict__ acc, const float* __restrict__ g90, float gamma90,
+            GradPrep* __restrict__ prep) {
+    const int si = blockIdx.x;
+    const int s = slice_of(d.sel, si);
+    const float gmax = key2f(acc[si].gmax_key);
+    const double last = (double)gmax + 1e-8;      // np.histogram range upper edge (python float)
+    const int i = threadIdx.x;
+    if (i < 128) {
+        const double step = last / 128.0;         // np.linspace in float64, then cast to float32
+        prep[si].edges[i] = (float)((double)i * step + 0.0);
+    } else if (i == 128) {
+        prep[si].edges[128] = (float)last;
+    } else if (i == 129) {
+        prep[si].denom = (float)last;
+        prep[si].last = (float)last;
+        prep[si].thr_edge = gmax > 0.0f ? __fmul_rn(0.1f, gmax) : 0.0f;
+        prep[si].t90 = lerp_np(g90[s * 2], g90[s * 2 + 1], gamma90);
+    }
+}
+
+__global__ void __launch_bounds__(NT)
+k_grad_pass(const float* __restrict__ gbuf, Dims d, const GradPrep* __restrict__ prep,
+            MetAcc* __restrict__ acc) {
+    __shared__ float edges[129];
+    __shared__ unsigned h[128];
+    __shared__ double red[32];
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const GradPrep& P = prep[si];
+    for (int i = tid; i < 129; i += NT) edges[i] = P.edges[i];
+    for (int i = tid; i < 128; i += NT) h[i] = 0;
+    const float denom = P.denom, last = P.last, thr = P.thr_edge, t90 = P.t90;
+    __syncthreads();
+    const float* g = gbuf + (size_t)s * d.h * d.w;
+    const int len = d.h * d.w;
+    unsigned c_edge = 0, c_strong = 0;
+    double s_strong[1] = {0.0};
+    for (int i = blockIdx.x * NT + tid; i < len; i += gridDim.x * NT) {
+        const float v = g[i];
+        c_edge += (v > thr);
+        if (v >= t90) { c_strong++; s_strong[0] += (double)v; }
+        if (v >= 0.0f && v <= last) {
+            int b = (int)__fmul_rn(__fdiv_rn(v, denom), 128.0f);
+            if (b == 128) b = 127;
+            if (v < edges[b]) b -= 1;
+            if (b != 127 && v >= edges[b + 1]) b += 1;
+            unsigned am = __activemask();
+            unsigned peers = __match_any_sync(am, b);
+            if (lane == __ffs(peers) - 1) atomicAdd(&h[b], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    block_sum<1>(s_strong, red);
+    c_edge = warp_sum_u(c_edge);
+    c_strong = warp_sum_u(c_strong);
+    MetAcc* A = acc + si;
+    if (lane == 0) {
+        if (c_edge) atomicAdd(&A->cnt_edge, (unsigned long long)c_edge);
+        if (c_strong) atomicAdd(&A->cnt_strong, (unsigned long long)c_strong);
+    }
+    if (tid == 0) atomicAdd(&A->sum_strong, s_strong[0]);
+    for (int i = tid; i < 128; i += NT) { unsigned v = h[i]; if (v) atomicAdd(&A->hist128[i], v); }
+}
+
+// ---------------------------------------------------------------------------------------
+// Finalisation: one block per slice.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double f32r(double v) { return (double)(float)v; }
+
+__device__ double block_entropy(const unsigned* hist, int nb, double* red) {
+    // -sum p log2 p over non-empty bins, p = c / sum(c)
+    double tot[1] = {0.0};
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) tot[0] += (double)hist[i];
+    block_sum<1>(tot, red);
+    __shared__ double total_s;
+    if (threadIdx.x == 0) total_s = tot[0];
+    __syncthreads();
+    const double total = total_s;
+    double e[1] = {0.0};
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        unsigned c = hist[i];
+        if (c) { double p = (double)c / total; e[0] += p * log2(p); }
+    }
+    block_sum<1>(e, red);
+    __shared__ double ent_s;
+    if (threadIdx.x == 0) ent_s = total > 0.0 ? -e[0] : 0.0;
+    __syncthreads();
+    return ent_s;
+}
+
+__global__ void __launch_bounds__(NT)
+k_finalize(Dims d, const MetAcc* __restrict__ acc, const float* __restrict__ xsel, PctPlan plan,
+           const double* __restrict__ sigma_arr, const GradPrep* __restrict__ prep, int flags,
+           double* __restrict__ out) {
+    __shared__ double red[32];
+    const int si = blockIdx.x;
+    const int s = slice_of(d.sel, si);
+    const MetAcc& A = acc[si];
+    const double ent = block_entropy(A.hist256, 256, red);
+    const double gent = block_entropy(A.hist128, 128, red);
+    if (threadIdx.x != 0) return;
+    const double N = (double)d.h * (double)d.w;
+    double* o = out + (size_t)s * MC_COLS;
+    const double sigma = sigma_arr[s];
+    const double mean = A.sum_x / N;
+    const double var = fmax(A.sum_x2 / N - mean * mean, 0.0);
+    const double lmean = A.sum_lap / N;
+    const double lap_var = fmax(A.sum_lap2 / N - lmean * lmean, 0.0);
+    const double gmean = A.sum_g / N;
+    const double gvar = fmax(A.sum_g2 / N - gmean * gmean, 0.0);
+    const double lsm = A.sum_ls / N;
+    const double lsv = fmax(A.sum_ls2 / N - lsm * lsm, 0.0);
+    const float* xs = xsel + (size_t)s * 8;
+    const float p05 = lerp_np(xs[0], xs[1], plan.gamma[0]);
+    const float p25 = lerp_np(xs[2], xs[3], plan.gamma[1]);
+    const float p75 = lerp_np(xs[4], xs[5], plan.gamma[2]);
+    const float p95 = lerp_np(xs[6], xs[7], plan.gamma[3]);
+    const double sden = fmax(sigma, 1e-8);
+
+    o[MC_SIGMA] = sigma;
+    o[MC_LAP_VAR] = f32r(lap_var);
+    o[MC_STD] = f32r(sqrt(var));
+    o[MC_PCT_LOW] = (double)A.cnt_low / N;
+    o[MC_PCT_HIGH] = (double)A.cnt_high / N;
+    o[MC_ENTROPY] = ent;
+    o[MC_EDGE_DENSITY] = (double)A.cnt_edge / N;
+    o[MC_GRAD_MEAN] = f32r(gmean);
+    o[MC_GRAD_STD] = f32r(sqrt(gvar));
+    // np.float32 mean / python float -> float32 division
+    o[MC_SNR] = (double)__fdiv_rn((float)mean, (float)sden);
+    o[MC_CNR] = ((double)p95 - (double)p05) / sden;
+    o[MC_LAP_ENERGY] = f32r(A.sum_lap2 / N);
+    o[MC_HIST_SPREAD] = (double)p75 - (double)p25;
+    o[MC_LOCAL_CONTRAST] = f32r(sqrt(lsv));
+    o[MC_GRAD_STRENGTH] = A.cnt_strong ? f32r(A.sum_strong / (double)A.cnt_strong) : 0.0;
+    o[MC_GRAD_ENTROPY] = gent;
+    o[MC_MEAN] = f32r(mean);
+    const float ml = (float)(A.sum_abslap / N), mg = (float)gmean;
+    const float er = __fdiv_rn(ml, __fadd_rn(mg, 1e-8f));
+    o[MC_EDGE_RATIO] = (double)er;
+    if (flags & 1) {
+        const double lvm = A.box16[0] / N;
+        const double lvv = fmax(A.box16[1] / N - lvm * lvm, 0.0);
+        const float vov = __fdiv_rn((float)sqrt(lvv), __fadd_rn((float)lvm, 1e-8f));
+        o[MC_VAR_OF_VAR] = (double)vov;
+        o[MC_NIQE] = (double)vov + fmax(0.0, (double)er - 1.0) * 10.0;
+    } else {
+        o[MC_VAR_OF_VAR] = nan("");
+        o[MC_NIQE] = nan("");
+    }
+    o[MC_GMAX] = (double)key2f(A.gmax_key);
+    o[MC_P05] = (double)p05;
+    o[MC_P95] = (double)p95;
+    o[MC_RESERVED] = (double)prep[si].t90;
+}
+
+__global__ void k_quality_out(Dims d, const double* __restrict__ edge2, const double* __restrict__ box2,
+                              int flags, double* __restrict__ out) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= d.n_sel) return;
+    int s = slice_of(d.sel, si);
+    const double N = (double)d.h * (double)d.w;
+    const float ml = (float)(edge2[si * 2] / N), mg = (float)(edge2[si * 2 + 1] / N);
+    const float er = __fdiv_rn(ml, __fadd_rn(mg, 1e-8f));
+    out[s * 2] = (double)er;
+    if (flags & 1) {
+        const double lvm = box2[si * 2] / N;
+        const double lvv = fmax(box2[si * 2 + 1] / N - lvm * lvm, 0.0);
+        const float vov = __fdiv_rn((float)sqrt(lvv), __fadd_rn((float)lvm, 1e-8f));
+        out[s * 2 + 1] = (double)vov + fmax(0.0, (double)er - 1.0) * 10.0;
+    } else {
+        out[s * 2 + 1] = nan("");
+    }
+}
+
+__global__ void k_copy_box16(int n_sel, const double* __restrict__ box2, MetAcc* __restrict__ acc) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= n_sel) return;
+    acc[si].box16[0] = box2[si * 2];
+    acc[si].box16[1] = box2[si * 2 + 1];
+}
+
+struct SigmaBufs {
+    float* absdd; unsigned* l1; int* ranks; float* sel_out; void* sel_ws; size_t sel_ws_bytes;
+};
+
+void carve_sigma(Arena& a, int n, int n_sel, int hd, int wd, SigmaBufs& b) {
+    b.absdd = a.take<float>((size_t)n * hd * wd);
+    b.l1 = a.take<unsigned>((size_t)n_sel * SEL_L1_BINS);
+    b.ranks = a.take<int>((size_t)n * 2);
+    b.sel_out = a.take<float>((size_t)n * 2);
+    b.sel_ws_bytes = select_workspace_bytes(n_sel);
+    b.sel_ws = a.take<char>(b.sel_ws_bytes);
+}
+
+int sigma_core(const float* img, const Dims& d, MetAcc* acc, SigmaBufs& b, double* sigma_out,
+               cudaStream_t stream) {
+    const int hd = (d.h + 3) / 2, wd = (d.w + 3) / 2;
+    cudaMemsetAsync(b.l1, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
+    dim3 grid(((wd + DT - 1) / DT) * ((hd + DT - 1) / DT), d.n_sel);
+    MDIMG_LAUNCH k_db2_dd<<<grid, NT, 0, stream>>>(img, d, hd, wd, b.absdd, b.l1, acc);
+    MDIMG_LAUNCH k_sigma_ranks<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, hd * wd, acc, b.ranks);
+    int rc = select_run(b.absdd, (long long)hd * wd, hd * wd, d, 2, b.ranks, b.l1, b.sel_out,
+                        b.sel_ws, b.sel_ws_bytes, stream);
+    if (rc) return rc;
+    MDIMG_LAUNCH k_sigma_out<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, b.sel_out, sigma_out);
+    return check_launch("estimate_sigma");
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// Host entry points (internal C++; the C-ABI wrappers live in api.cu)
+// ---------------------------------------------------------------------------------------
+size_t sigma_workspace_bytes(int n_sel, int h, int w) {
+    // sized for n == n_sel is not enough when sel indexes a larger stack; api.cu passes n.
+    Arena a(nullptr, 0);
+    SigmaBufs b;
+    a.take<MetAcc>(n_sel);
+    carve_sigma(a, n_sel, n_sel, (h + 3) / 2, (w + 3) / 2, b);
+    return a.off;
+}
+
+int sigma_run(const float* img, const Dims& d, double* sigma_out, void* ws, size_t ws_bytes,
+              cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    Arena a(ws, ws_bytes);
+    MetAcc* acc = a.take<MetAcc>(d.n_sel);
+    SigmaBufs b;
+    carve_sigma(a, d.n, d.n_sel, (d.h + 3) / 2, (d.w + 3) / 2, b);
+    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "estimate_sigma: workspace too small (%zu > %zu)", a.off, ws_bytes);
+    cudaMemsetAsync(acc, 0, sizeof(MetAcc) * d.n_sel, stream);
+    return sigma_core(img, d, acc, b, sigma_out, stream);
+}
+
+size_t quality_workspace_bytes(int n_sel, int h, int w) {
+    (void)h; (void)w;
+    Arena a(nullptr, 0);
+    a.take<double>((size_t)n_sel * 2);
+    a.take<double>((size_t)n_sel * 2);
+    return a.off;
+}
+
+int quality_run(const float* img, const Dims& d, int flags, double* out, void* ws, size_t ws_bytes,
+                cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    Arena a(ws, ws_bytes);
+    double* edge2 = a.take<double>((size_t)d.n_sel * 2);
+    double* box2 = a.take<double>((size_t)d.n_sel * 2);
+    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "quality: workspace too small");
+    cudaMemsetAsync(edge2, 0, sizeof(double) * 2 * d.n_sel, stream);
+    cudaMemsetAsync(box2, 0, sizeof(double) * 2 * d.n_sel, stream);
+    dim3 grid(((d.w + EW - 1) / EW) * ((d.h + EH - 1) / EH), d.n_sel);
+    MDIMG_LAUNCH k_edge_stats<<<grid, NT, 0, stream>>>(img, d, edge2);
+    if (flags & 1) launch_box16_stats(img, d, box2, stream);
+    MDIMG_LAUNCH k_quality_out<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, edge2, box2, flags, out);
+    return check_launch("quality");
+}
+
+namespace {
+struct MetBufs {
+    MetAcc* acc; float* g; unsigned* l1x; unsigned* l1g; int* plan_ranks; int* xranks; int* granks;
+    float* xsel; float* gsel; GradPrep* prep; double* sigma; double* box2;
+    void* sel_ws; size_t sel_ws_bytes; SigmaBufs sb;
+};
+void carve_metrics(Arena& a, int n, int n_sel, int h, int w, MetBufs& m) {
+    m.acc = a.take<MetAcc>(n_sel);
+    m.g = a.take<float>((size_t)n * h * w);
+    m.l1x = a.take<unsigned>((size_t)n_sel * SEL_L1_BINS);
+    m.l1g = a.take<unsigned>((size_t)n_sel * SEL_L1_BINS);
+    m.plan_ranks = a.take<int>(16);
+    m.xranks = a.take<int>((size_t)n * 8);
+    m.granks = a.take<int>((size_t)n * 2);
+    m.xsel = a.take<float>((size_t)n * 8);
+    m.gsel = a.take<float>((size_t)n * 2);
+    m.prep = a.take<GradPrep>(n_sel);
+    m.sigma = a.take<double>(n);
+    m.box2 = a.take<double>((size_t)n_sel * 2);
+    m.sel_ws_bytes = select_workspace_bytes(n_sel);
+    m.sel_ws = a.take<char>(m.sel_ws_bytes);
+    carve_sigma(a, n, n_sel, (h + 3) / 2, (w + 3) / 2, m.sb);
+}
+}  // namespace
+
+size_t metrics_workspace_bytes(int n_sel, int h, int w) {
+    Arena a(nullptr, 0);
+    MetBufs m;
+    carve_metrics(a, n_sel, n_sel, h, w, m);
+    return a.off;
+}
+
+int metrics_run(const float* img, const Dims& d, const PctPlan& plan, int flags, double* out,
+                void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    Arena a(ws, ws_bytes);
+    MetBufs m;
+    carve_metrics(a, d.n, d.n_sel, d.h, d.w, m);
+    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "metrics: workspace too small (%zu > %zu)", a.off, ws_bytes);
+    const int len = d.h * d.w;
+
+    cudaMemsetAsync(m.acc, 0, sizeof(MetAcc) * d.n_sel, stream);
+    cudaMemsetAsync(m.l1x, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
+    cudaMemsetAsync(m.l1g, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_stencil_stats, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(StencilSmem));
+        attr_set = true;
+    }
+    dim3 grid(((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH), d.n_sel);
+    MDIMG_LAUNCH k_stencil_stats<<<grid, NT, sizeof(StencilSmem), stream>>>(img, d, m.acc, m.g, m.l1x, m.l1g);
+    int rc = check_launch("stencil_stats");
+    if (rc) return rc;
+
+    // sigma (db2 'dd' median)
+    rc = sigma_core(img, d, m.acc, m.sb, m.sigma, stream);
+    if (rc) return rc;
+
+    // percentiles of x: ranks (lo,hi) for 5, 25, 75, 95; of |grad|: 90
+    int host_ranks[10];
+    for (int k = 0; k < 4; ++k) { host_ranks[2 * k] = plan.lo[k]; host_ranks[2 * k + 1] = plan.hi[k]; }
+    host_ranks[8] = plan.lo[4]; host_ranks[9] = plan.hi[4];
+    cudaMemcpyAsync(m.plan_ranks, host_ranks, sizeof(host_ranks), cudaMemcpyHostToDevice, stream);
+    MDIMG_LAUNCH k_fill_ranks<<<(d.n_sel * 8 + 127) / 128, 128, 0, stream>>>(d, 8, m.plan_ranks, m.xranks);
+    MDIMG_LAUNCH k_fill_ranks<<<(d.n_sel * 2 + 127) / 128, 128, 0, stream>>>(d, 2, m.plan_ranks + 8, m.granks);
+    rc = select_run(img, (long long)len, len, d, 8, m.xranks, m.l1x, m.xsel, m.sel_ws, m.sel_ws_bytes, stream);
+    if (rc) return rc;
+    rc = select_run(m.g, (long long)len, len, d, 2, m.granks, m.l1g, m.gsel, m.sel_ws, m.sel_ws_bytes, stream);
+    if (rc) return rc;
+
+    MDIMG_LAUNCH k_grad_prep<<<d.n_sel, 160, 0, stream>>>(d, m.acc, m.gsel, plan.gamma[4], m.prep);
+    int bx = (len + NT * 8 - 1) / (NT * 8);
+    if (bx > 512) bx = 512;
+    MDIMG_LAUNCH k_grad_pass<<<dim3(bx, d.n_sel), NT, 0, stream>>>(m.g, d, m.prep, m.acc);
+
+    if (flags & 1) {
+        cudaMemsetAsync(m.box2, 0, sizeof(double) * 2 * d.n_sel, stream);
+        launch_box16_stats(img, d, m.box2, stream);
+        MDIMG_LAUNCH k_copy_box16<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d.n_sel, m.box2, m.acc);
+    }
+    MDIMG_LAUNCH k_finalize<<<d.n_sel, NT, 0, stream>>>(d, m.acc, m.xsel, plan, m.sigma, m.prep, flags, out);
+    return check_launch("metrics");
+}
+
+}  // namespace mdimg

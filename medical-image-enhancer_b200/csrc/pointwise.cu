@@ -1,0 +1,271 @@
+// Elementwise and reduction kernels: per-slice min/max, normalize_image
+// (pipeline/dicom_io.py:84-91), adjust_gamma (skimage, called at pipeline/enhancement.py:194,197,
+// 284,336), the blends of _light_denoise / the over-processing guard (enhancement.py:93,365) and
+// np.clip(., 0, 1) (enhancement.py:218,314,352).  All are one read + one write of the slice,
+// 128-bit vectorised when the slice length is a multiple of 4.
+#include "enhance.cuh"
+
+namespace mdimg {
+
+namespace {
+
+constexpr int NT = 256;
+
+inline int blocks_for(long long len, int per_thread) {
+    long long b = (len + (long long)NT * per_thread - 1) / ((long long)NT * per_thread);
+    if (b < 1) b = 1;
+    if (b > 4096) b = 4096;
+    return (int)b;
+}
+
+// ---------------- min / max ----------------
+__global__ void k_mm_init(Dims d, uint2* __restrict__ mm) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= d.n_sel) return;
+    mm[slice_of(d.sel, si)] = make_uint2(0xFFFFFFFFu, 0u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+k_minmax(const T* __restrict__ img, Dims d, uint2* __restrict__ mm) {
+    __shared__ float smin[NT / 32], smax[NT / 32];
+    const int s = slice_of(d.sel, blockIdx.y);
+    const long long len = d.px();
+    const T* p = img + (size_t)s * len;
+    float lo = INFINITY, hi = -INFINITY;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < len; i += (long long)gridDim.x * NT) {
+        float v = (float)p[i];
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { smin[wid] = lo; smax[wid] = hi; }
+    __syncthreads();
+    if (wid == 0) {
+        lo = lane < NT / 32 ? smin[lane] : INFINITY;
+        hi = lane < NT / 32 ? smax[lane] : -INFINITY;
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (lane == 0) {
+            atomicMin(&mm[s].x, f2key(lo));
+            atomicMax(&mm[s].y, f2key(hi));
+        }
+    }
+}
+
+__global__ void k_mm_decode(Dims d, const uint2* __restrict__ mm, float* __restrict__ out2) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= d.n_sel) return;
+    int s = slice_of(d.sel, si);
+    out2[s * 2] = key2f(mm[s].x);
+    out2[s * 2 + 1] = key2f(mm[s].y);
+}
+
+// ---------------- generic elementwise driver ----------------
+// F: struct with `__device__ bool prepare(int s)` (returns false to skip the slice) and
+// `__device__ float apply(float a, float b)`.
+template <typename F, bool TWO>
+__global__ void __launch_bounds__(NT)
+k_map(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, Dims d, F f) {
+    const int s = slice_of(d.sel, blockIdx.y);
+    if (!f.prepare(s)) return;
+    const long long len = d.px();
+    const size_t base = (size_t)s * len;
+    const float* pa = a + base;
+    const float* pb = TWO ? b + base : nullptr;
+    float* po = out + base;
+    const bool aligned = (((uintptr_t)pa | (uintptr_t)po | (TWO ? (uintptr_t)pb : 0)) & 15) == 0;
+    if ((len & 3) == 0 && aligned) {
+        const long long n4 = len >> 2;
+        const float4* a4 = reinterpret_cast<const float4*>(pa);
+        const float4* b4 = reinterpret_cast<const float4*>(pb);
+        float4* o4 = reinterpret_cast<float4*>(po);
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
+            float4 va = a4[i];
+            float4 vb = TWO ? b4[i] : make_float4(0, 0, 0, 0);
+            float4 r;
+            r.x = f.apply(va.x, vb.x); r.y = f.apply(va.y, vb.y);
+            r.z = f.apply(va.z, vb.z); r.w = f.apply(va.w, vb.w);
+            o4[i] = r;
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < len; i += (long long)gridDim.x * NT)
+            po[i] = f.apply(pa[i], TWO ? pb[i] : 0.0f);
+    }
+}
+
+struct NormF {
+    const uint2* mm; float lo, denom; bool zero;
+    __device__ bool prepare(int s) {
+        float mn = key2f(mm[s].x), mx = key2f(mm[s].y);
+        zero = ((double)mx - (double)mn) < 1e-8;
+        lo = mn;
+        denom = (float)((double)mx - (double)mn);   // python-float difference used as a float32 scalar
+        return true;
+    }
+    __device__ float apply(float a, float) const {
+        return zero ? 0.0f : __fdiv_rn(__fsub_rn(a, lo), denom);
+    }
+};
+
+__global__ void __launch_bounds__(NT)
+k_normalize_u16(const uint16_t* __restrict__ in, float* __restrict__ out, Dims d,
+                const uint2* __restrict__ mm) {
+    const int s = slice_of(d.sel, blockIdx.y);
+    NormF f; f.mm = mm; f.prepare(s);
+    const long long len = d.px();
+    const uint16_t* p = in + (size_t)s * len;
+    float* o = out + (size_t)s * len;
+    const bool aligned = (((uintptr_t)p & 7) == 0) && (((uintptr_t)o & 15) == 0);
+    if ((len & 3) == 0 && aligned) {
+        const long long n4 = len >> 2;
+        const ushort4* p4 = reinterpret_cast<const ushort4*>(p);
+        float4* o4 = reinterpret_cast<float4*>(o);
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
+            ushort4 v = p4[i];
+            float4 r;
+            r.x = f.apply((float)v.x, 0); r.y = f.apply((float)v.y, 0);
+            r.z = f.apply((float)v.z, 0); r.w = f.apply((float)v.w, 0);
+            o4[i] = r;
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < len; i += (long long)gridDim.x * NT)
+            o[i] = f.apply((float)p[i], 0);
+    }
+}
+
+struct GammaF {
+    const uint2* mm; int* neg_flag; double gamma;
+    __device__ bool prepare(int s) {
+        if (mm && key2f(mm[s].x) < 0.0f) {     // _assert_non_negative -> ValueError in the reference
+            if (threadIdx.x == 0 && blockIdx.x == 0) neg_flag[s] = 1;
+            return false;
+        }
+        return true;
+    }
+    // float32 power: evaluated in double and rounded once (a correctly rounded powf)
+    __device__ float apply(float a, float) const { return (float)pow((double)a, gamma); }
+};
+
+struct AxpbyF {
+    float c0, c1; int clip;
+    __device__ bool prepare(int) { return true; }
+    __device__ float apply(float a, float b) const {
+        float r = __fadd_rn(__fmul_rn(c0, a), __fmul_rn(c1, b));
+        if (clip) r = fminf(fmaxf(r, 0.0f), 1.0f);
+        return r;
+    }
+};
+
+struct BlendSkipF {      // _light_denoise: (1-k)*x + k*den, or x itself where the slice was skipped
+    float c0, c1; const int* skip; const double* sigma; int* skipped_out; bool ident;
+    __device__ bool prepare(int s) {
+        ident = skip[s] != 0;
+        if (skipped_out && threadIdx.x == 0 && blockIdx.x == 0) skipped_out[s] = ident ? 1 : 0;
+        return true;
+    }
+    __device__ float apply(float a, float b) const {
+        return ident ? a : __fadd_rn(__fmul_rn(c0, a), __fmul_rn(c1, b));
+    }
+};
+
+__global__ void k_skip_flags(Dims d, const double* __restrict__ sigma, double thresh, int* __restrict__ skip) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= d.n_sel) return;
+    int s = slice_of(d.sel, si);
+    skip[s] = sigma[s] < thresh ? 1 : 0;      // NaN compares false, as in the reference
+}
+
+struct ClipF {
+    __device__ bool prepare(int) { return true; }
+    __device__ float apply(float a, float) const { return fminf(fmaxf(a, 0.0f), 1.0f); }
+};
+
+struct CopyF {
+    __device__ bool prepare(int) { return true; }
+    __device__ float apply(float a, float) const { return a; }
+};
+
+}  // namespace
+
+int minmax_f32_run(const float* img, const Dims& d, uint2* mm, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    MDIMG_LAUNCH k_mm_init<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, mm);
+    MDIMG_LAUNCH k_minmax<float><<<dim3(blocks_for(d.px(), 16), d.n_sel), NT, 0, stream>>>(img, d, mm);
+    return check_launch("minmax_f32");
+}
+
+int minmax_u16_run(const uint16_t* img, const Dims& d, uint2* mm, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    MDIMG_LAUNCH k_mm_init<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, mm);
+    MDIMG_LAUNCH k_minmax<uint16_t><<<dim3(blocks_for(d.px(), 16), d.n_sel), NT, 0, stream>>>(img, d, mm);
+    return check_launch("minmax_u16");
+}
+
+int minmax_decode_run(const uint2* mm, const Dims& d, float* out2, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    MDIMG_LAUNCH k_mm_decode<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, mm, out2);
+    return check_launch("minmax_decode");
+}
+
+int normalize_u16_run(const uint16_t* in, float* out, const Dims& d, const uint2* mm, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    MDIMG_LAUNCH k_normalize_u16<<<dim3(blocks_for(d.px(), 8), d.n_sel), NT, 0, stream>>>(in, out, d, mm);
+    return check_launch("normalize_u16");
+}
+
+int normalize_f32_run(const float* in, float* out, const Dims& d, const uint2* mm, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    NormF f; f.mm = mm; f.lo = 0; f.denom = 1; f.zero = false;
+    MDIMG_LAUNCH k_map<NormF, false><<<dim3(blocks_for(d.px(), 8), d.n_sel), NT, 0, stream>>>(in, nullptr, out, d, f);
+    return check_launch("normalize_f32");
+}
+
+int gamma_run(const float* in, float* out, const Dims& d, double gamma, const uint2* mm,
+              int* neg_flag, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    if (gamma < 0) return set_error(MDIMG_ERR_INVALID, "Gamma should be a non-negative real number.");
+    GammaF f; f.mm = mm; f.neg_flag = neg_flag; f.gamma = gamma;
+    MDIMG_LAUNCH k_map<GammaF, false><<<dim3(blocks_for(d.px(), 4), d.n_sel), NT, 0, stream>>>(in, nullptr, out, d, f);
+    return check_launch("gamma");
+}
+
+int axpby_run(const float* a, const float* b, float* out, const Dims& d, float c0, float c1,
+              int clip01, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    AxpbyF f; f.c0 = c0; f.c1 = c1; f.clip = clip01;
+    MDIMG_LAUNCH k_map<AxpbyF, true><<<dim3(blocks_for(d.px(), 8), d.n_sel), NT, 0, stream>>>(a, b, out, d, f);
+    return check_launch("axpby");
+}
+
+int blend_skip_run(const float* a, const float* b, float* out, const Dims& d, float c0, float c1,
+                   const int* skip, int* skipped_out, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    BlendSkipF f; f.c0 = c0; f.c1 = c1; f.skip = skip; f.sigma = nullptr; f.skipped_out = skipped_out; f.ident = false;
+    MDIMG_LAUNCH k_map<BlendSkipF, true><<<dim3(blocks_for(d.px(), 8), d.n_sel), NT, 0, stream>>>(a, b, out, d, f);
+    return check_launch("blend_skip");
+}
+
+int skip_flags_run(const Dims& d, const double* sigma, double thresh, int* skip, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    MDIMG_LAUNCH k_skip_flags<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, sigma, thresh, skip);
+    return check_launch("skip_flags");
+}
+
+int clip01_run(const float* in, float* out, const Dims& d, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    ClipF f;
+    MDIMG_LAUNCH k_map<ClipF, false><<<dim3(blocks_for(d.px(), 8), d.n_sel), NT, 0, stream>>>(in, nullptr, out, d, f);
+    return check_launch("clip01");
+}
+
+int copy_run(const float* in, float* out, const Dims& d, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    CopyF f;
+    MDIMG_LAUNCH k_map<CopyF, false><<<dim3(blocks_for(d.px(), 8), d.n_sel), NT, 0, stream>>>(in, nullptr, out, d, f);
+    return check_launch("copy");
+}
+
+}  // namespace mdimg

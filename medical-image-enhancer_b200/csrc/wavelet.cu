@@ -1,0 +1,396 @@
+// Wavelet denoise: skimage.restoration.denoise_wavelet(image, channel_axis=None,
+// rescale_sigma=True, mode=soft|hard[, sigma=...]) as called at pipeline/enhancement.py:86,169,
+// 270,328 — PyWavelets 'db1' (Haar) pyramid, L = max(floor(log2(min(h, w))) - 3, 1) levels,
+// BayesShrink threshold per detail band, soft / hard shrink, inverse transform.
+//
+// Arithmetic follows pywt: the forward transform accumulates in float32
+// (out[o] = f[0]*x[2o+1] + f[1]*x[2o], axis 0 then axis 1, symmetric extension on odd lengths);
+// the inverse runs axis 1 then axis 0 as lo*a + hi*d.  numpy >= 2 promotion decides the
+// precision of the inverse: with an estimated sigma (a float64 scalar) and soft shrinkage the
+// shrunk details and therefore the whole inverse are float64; with a caller-supplied python-float
+// sigma (the _light_denoise path) or hard shrinkage everything stays float32.
+//
+// This is the general per-level implementation (any size, odd lengths included): one kernel per
+// level on the way down (also accumulates the band energies and the finest 'dd' histogram), a tiny
+// threshold kernel, one kernel per level on the way up with the shrinkage fused into the load.
+#include "enhance.cuh"
+#include "select.cuh"
+
+namespace mdimg {
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int MAXL = 14;
+constexpr double SQ = 0.7071067811865476;
+
+struct Pyramid {
+    int L;
+    int H[MAXL + 1], W[MAXL + 1];
+    long long off[MAXL + 1];    // float offset of level l's three detail bands inside one slice
+    long long det_per_slice;    // floats
+    long long a_cap;            // floats per approximation ping-pong buffer
+    long long r_cap;            // elements per reconstruction ping-pong buffer
+};
+
+Pyramid make_pyramid(int h, int w) {
+    Pyramid p;
+    int m = h < w ? h : w;
+    int lg = 0;
+    while ((1 << (lg + 1)) <= m) ++lg;
+    p.L = lg - 3 > 1 ? lg - 3 : 1;
+    if (p.L > MAXL) p.L = MAXL;
+    p.H[0] = h; p.W[0] = w;
+    long long o = 0;
+    for (int l = 1; l <= p.L; ++l) {
+        p.H[l] = (p.H[l - 1] + 1) / 2;
+        p.W[l] = (p.W[l - 1] + 1) / 2;
+        p.off[l] = o;
+        o += 3LL * p.H[l] * p.W[l];
+    }
+    p.det_per_slice = o;
+    p.a_cap = (long long)p.H[1] * p.W[1];
+    p.r_cap = (long long)(p.H[1] + 2) * (p.W[1] + 2);
+    return p;
+}
+
+struct WaveAcc {                 // per slice (position in sel)
+    double energy[MAXL + 1][3];  // sum of float32 squares per detail band (ad, da, dd)
+    double thr[MAXL + 1][3];     // BayesShrink thresholds
+    double sigma;
+    unsigned dd_zero;
+    unsigned pad;
+};
+
+// ---- forward level -------------------------------------------------------------------------
+// in: level l-1 approximation (h0 x w0, pitch w0).  First level reads the image (slice id `s`),
+// deeper levels read the compact ping-pong buffer (index `si`).
+template <bool FIRST>
+__global__ void __launch_bounds__(NT)
+k_haar_fwd(const float* __restrict__ in, long long in_stride, int h0, int w0, Dims d,
+           const int* __restrict__ skip, int level, float* __restrict__ aout, long long a_stride,
+           float* __restrict__ det, long long det_stride, long long det_off,
+           WaveAcc* __restrict__ acc, unsigned* __restrict__ l1, int want_hist) {
+    __shared__ unsigned hh[SEL_L1_BINS];
+    __shared__ double red[3 * 32];
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    if (skip && skip[s]) return;
+    const int h1 = (h0 + 1) / 2, w1 = (w0 + 1) / 2;
+    const float* src = in + (size_t)(FIRST ? s : si) * in_stride;
+    float* ao = aout + (size_t)si * a_stride;
+    float* db = det + (size_t)si * det_stride + det_off;
+    const long long band = (long long)h1 * w1;
+    const float S = (float)SQ, NS = -(float)SQ;
+    const bool hist = FIRST && want_hist;
+    if (hist) for (int i = threadIdx.x; i < SEL_L1_BINS; i += NT) hh[i] = 0;
+    if (hist) __syncthreads();
+    double e[3] = {0.0, 0.0, 0.0};
+    unsigned nz = 0;
+    const long long total = band;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int y = (int)(i / w1), x = (int)(i - (long long)y * w1);
+        const int r0 = 2 * y, r1 = min(2 * y + 1, h0 - 1);
+        const int c0 = 2 * x, c1 = min(2 * x + 1, w0 - 1);
+        const float v00 = src[(size_t)r0 * w0 + c0], v01 = src[(size_t)r0 * w0 + c1];
+        const float v10 = src[(size_t)r1 * w0 + c0], v11 = src[(size_t)r1 * w0 + c1];
+        // axis 0
+        const float lo0 = __fadd_rn(__fmul_rn(S, v10), __fmul_rn(S, v00));
+        const float lo1 = __fadd_rn(__fmul_rn(S, v11), __fmul_rn(S, v01));
+        const float hi0 = __fadd_rn(__fmul_rn(NS, v10), __fmul_rn(S, v00));
+        const float hi1 = __fadd_rn(__fmul_rn(NS, v11), __fmul_rn(S, v01));
+        // axis 1
+        const float aa = __fadd_rn(__fmul_rn(S, lo1), __fmul_rn(S, lo0));
+        const float ad = __fadd_rn(__fmul_rn(NS, lo1), __fmul_rn(S, lo0));
+        const float da = __fadd_rn(__fmul_rn(S, hi1), __fmul_rn(S, hi0));
+        const float dd = __fadd_rn(__fmul_rn(NS, hi1), __fmul_rn(S, hi0));
+        ao[i] = aa;
+        db[i] = ad;
+        db[band + i] = da;
+        db[2 * band + i] = dd;
+        e[0] += (double)__fmul_rn(ad, ad);
+        e[1] += (double)__fmul_rn(da, da);
+        e[2] += (double)__fmul_rn(dd, dd);
+        if (hist) {
+            const float a = fabsf(dd);
+            nz += (a == 0.0f);
+            atomicAdd(&hh[f2key(a) >> 21], 1u);
+        }
+    }
+    block_sum<3>(e, red);
+    WaveAcc* A = acc + si;
+    if (threadIdx.x == 0) {
+        atomicAdd(&A->energy[level][0], e[0]);
+        atomicAdd(&A->energy[level][1], e[1]);
+        atomicAdd(&A->energy[level][2], e[2]);
+    }
+    if (hist) {
+        nz = warp_sum_u(nz);
+        if ((threadIdx.x & 31) == 0 && nz) atomicAdd(&A->dd_zero, nz);
+        __syncthreads();
+        unsigned* g = l1 + (size_t)si * SEL_L1_BINS;
+        for (int i = threadIdx.x; i < SEL_L1_BINS; i += NT) { unsigned v = hh[i]; if (v) atomicAdd(&g[i], v); }
+    }
+}
+
+__global__ void k_wave_ranks(Dims d, int len, const WaveAcc* __restrict__ acc, int* __restrict__ ranks) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= d.n_sel) return;
+    int s = slice_of(d.sel, si);
+    int nz = (int)acc[si].dd_zero;
+    int m = len - nz;
+    if (m <= 0) { ranks[s * 2] = -1; ranks[s * 2 + 1] = -1; return; }
+    ranks[s * 2] = nz + (m - 1) / 2;
+    ranks[s * 2 + 1] = nz + m / 2;
+}
+
+// BayesShrink thresholds (skimage _bayes_thresh) for every level / band of every slice.
+__global__ void k_wave_thresholds(Dims d, Pyramid p, WaveAcc* __restrict__ acc,
+                                  const float* __restrict__ med_pair, const double* __restrict__ sigma_in,
+                                  double sigma_scale) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= d.n_sel) return;
+    int s = slice_of(d.sel, si);
+    WaveAcc& A = acc[si];
+    const float eps = 1.1920928955078125e-07f;   // np.finfo(np.float32).eps
+    if (sigma_in == nullptr) {
+        // sigma = np.float64: float32 median / norm.ppf(0.75)
+        const float med = __fdiv_rn(__fadd_rn(med_pair[s * 2], med_pair[s * 2 + 1]), 2.0f);
+        const double sigma = (double)med / 0.6744897501960817;
+        A.sigma = sigma;
+        const double var = sigma * sigma;
+        for (int l = 1; l <= p.L; ++l) {
+            const double cnt = (double)p.H[l] * (double)p.W[l];
+            for (int b = 0; b < 3; ++b) {
+                const float dvar = (float)(A.energy[l][b] / cnt);     // np.mean of float32 squares
+                const double diff = (double)dvar - var;               // float32 - float64 -> float64
+                double root;
+                if (diff >= (double)eps) root = sqrt(diff);           // max(diff, eps) keeps `diff` on ties
+                else if (diff != diff) root = diff;                   // NaN propagates through max()
+                else root = (double)sqrtf(eps);
+                A.thr[l][b] = var / root;
+            }
+        }
+    } else {
+        // sigma is a python float: everything around it stays float32 (NEP 50 weak scalar)
+        const double sigma = sigma_in[s] * sigma_scale;
+        A.sigma = sigma;
+        const double var = sigma * sigma;
+        const float varf = (float)var;
+        for (int l = 1; l <= p.L; ++l) {
+            const double cnt = (double)p.H[l] * (double)p.W[l];
+            for (int b = 0; b < 3; ++b) {
+                const float dvar = (float)(A.energy[l][b] / cnt);
+                float diff = __fsub_rn(dvar, varf);
+                float m = diff >= eps ? diff : (diff != diff ? diff : eps);
+                A.thr[l][b] = (double)__fdiv_rn(varf, __fsqrt_rn(m));
+            }
+        }
+    }
+}
+
+template <typename T> struct Ops;
+template <> struct Ops<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+template <> struct Ops<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+};
+
+// pywt.threshold on one coefficient.  MODE 0: soft with a float64 threshold (result float64);
+// 1: soft with a float32 threshold; 2: hard (data stays float32; the compare is exact).
+template <typename T, int MODE>
+__device__ __forceinline__ T shrink(float dcoef, double thr) {
+    if (MODE == 0) {
+        const double dv = (double)dcoef;
+        double f = __dsub_rn(1.0, __ddiv_rn(thr, fabs(dv)));
+        f = f < 0.0 ? 0.0 : f;           // ndarray.clip(min=0): NaN stays NaN
+        return (T)__dmul_rn(dv, f);
+    } else if (MODE == 1) {
+        float f = __fsub_rn(1.0f, __fdiv_rn((float)thr, fabsf(dcoef)));
+        f = f < 0.0f ? 0.0f : f;
+        return (T)__fmul_rn(dcoef, f);
+    } else {
+        return (T)(((double)fabsf(dcoef) < thr) ? 0.0f : dcoef);
+    }
+}
+
+// ---- inverse level -------------------------------------------------------------------------
+// ain: approximation at this level (float32 for the coarsest level, else T), read on [hd x wd]
+// with pitch a_pitch.  Writes the 2hd x 2wd reconstruction (pitch out_pitch), or, for the last
+// level, the cropped float32 image.
+template <typename T, typename TA, int MODE, bool LAST>
+__global__ void __launch_bounds__(NT)
+k_haar_inv(const TA* __restrict__ ain, long long a_stride, int a_pitch, int hd, int wd, Dims d,
+           const int* __restrict__ skip, int level, const float* __restrict__ det,
+           long long det_stride, long long det_off, const WaveAcc* __restrict__ acc,
+           T* __restrict__ rout, long long r_stride, int out_pitch,
+           const float* __restrict__ img_in, float* __restrict__ img_out) {
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    if (skip && skip[s]) {
+        if (LAST) {   // untouched slice: copy through
+            const long long len = d.px();
+            const float* a = img_in + (size_t)s * len;
+            float* o = img_out + (size_t)s * len;
+            if (a != o)
+                for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < len; i += (long long)gridDim.x * NT) o[i] = a[i];
+        }
+        return;
+    }
+    const TA* ap = ain + (size_t)si * a_stride;
+    const float* db = det + (size_t)si * det_stride + det_off;
+    const long long band = (long long)hd * wd;
+    const WaveAcc& A = acc[si];
+    const double t_ad = A.thr[level][0], t_da = A.thr[level][1], t_dd = A.thr[level][2];
+    const T S = (T)SQ, NS = -(T)SQ;
+    typedef Ops<T> O;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < band; i += (long long)gridDim.x * NT) {
+        const int y = (int)(i / wd), x = (int)(i - (long long)y * wd);
+        const T aa = (T)ap[(size_t)y * a_pitch + x];
+        const T ad = shrink<T, MODE>(db[i], t_ad);
+        const T da = shrink<T, MODE>(db[band + i], t_da);
+        const T dd = shrink<T, MODE>(db[2 * band + i], t_dd);
+        // axis 1: 'a' = idwt(aa, ad), 'd' = idwt(da, dd);  out[2x] = lo0*a + hi0*d, out[2x+1] = lo1*a + hi1*d
+        const T a_e = O::add(O::mul(S, aa), O::mul(S, ad));
+        const T a_o = O::add(O::mul(S, aa), O::mul(NS, ad));
+        const T d_e = O::add(O::mul(S, da), O::mul(S, dd));
+        const T d_o = O::add(O::mul(S, da), O::mul(NS, dd));
+        // axis 0
+        const T o00 = O::add(O::mul(S, a_e), O::mul(S, d_e));
+        const T o10 = O::add(O::mul(S, a_e), O::mul(NS, d_e));
+        const T o01 = O::add(O::mul(S, a_o), O::mul(S, d_o));
+        const T o11 = O::add(O::mul(S, a_o), O::mul(NS, d_o));
+        if (LAST) {
+            float* o = img_out + (size_t)s * d.h * d.w;
+            const int Y = 2 * y, X = 2 * x;
+            if (Y < d.h && X < d.w) o[(size_t)Y * d.w + X] = (float)o00;
+            if (Y < d.h && X + 1 < d.w) o[(size_t)Y * d.w + X + 1] = (float)o01;
+            if (Y + 1 < d.h && X < d.w) o[(size_t)(Y + 1) * d.w + X] = (float)o10;
+            if (Y + 1 < d.h && X + 1 < d.w) o[(size_t)(Y + 1) * d.w + X + 1] = (float)o11;
+        } else {
+            T* o = rout + (size_t)si * r_stride;
+            const size_t b0 = (size_t)(2 * y) * out_pitch + 2 * x;
+            o[b0] = o00; o[b0 + 1] = o01;
+            o[b0 + out_pitch] = o10; o[b0 + out_pitch + 1] = o11;
+        }
+    }
+}
+
+struct WaveBufs {
+    WaveAcc* acc; float* det; float* a0; float* a1; double* r0; double* r1;
+    unsigned* l1; int* ranks; float* med; void* sel_ws; size_t sel_ws_bytes;
+};
+
+void carve(Arena& a, int n, int n_sel, const Pyramid& p, WaveBufs& b) {
+    b.acc = a.take<WaveAcc>(n_sel);
+    b.det = a.take<float>((size_t)n_sel * p.det_per_slice);
+    b.a0 = a.take<float>((size_t)n_sel * p.a_cap);
+    b.a1 = a.take<float>((size_t)n_sel * p.a_cap);
+    b.r0 = a.take<double>((size_t)n_sel * p.r_cap);
+    b.r1 = a.take<double>((size_t)n_sel * p.r_cap);
+    b.l1 = a.take<unsigned>((size_t)n_sel * SEL_L1_BINS);
+    b.ranks = a.take<int>((size_t)n * 2);
+    b.med = a.take<float>((size_t)n * 2);
+    b.sel_ws_bytes = select_workspace_bytes(n_sel);
+    b.sel_ws = a.take<char>(b.sel_ws_bytes);
+}
+
+inline int grid_x(long long items) {
+    long long g = (items + NT * 4 - 1) / (NT * 4);
+    if (g < 1) g = 1;
+    if (g > 2048) g = 2048;
+    return (int)g;
+}
+
+template <typename T, int MODE>
+void run_inverse(const Pyramid& p, const Dims& d, const int* skip, const WaveBufs& b,
+                 const float* coarse, const float* img_in, float* img_out, cudaStream_t st) {
+    T* r[2] = {reinterpret_cast<T*>(b.r0), reinterpret_cast<T*>(b.r1)};
+    int cur = 0;
+    for (int l = p.L; l >= 1; --l) {
+        const int hd = p.H[l], wd = p.W[l];
+        dim3 grid(grid_x((long long)hd * wd), d.n_sel);
+        const bool last = (l == 1);
+        const bool first = (l == p.L);
+        const int out_pitch = 2 * wd;
+        T* rout = r[cur];
+        if (first) {
+            if (last)
+                MDIMG_LAUNCH k_haar_inv<T, float, MODE, true><<<grid, NT, 0, st>>>(coarse, p.a_cap, wd, hd, wd, d, skip, l,
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out);
+            else
+                MDIMG_LAUNCH k_haar_inv<T, float, MODE, false><<<grid, NT, 0, st>>>(coarse, p.a_cap, wd, hd, wd, d, skip, l,
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out);
+        } else {
+            const T* ain = r[cur ^ 1];
+            const int a_pitch = 2 * p.W[l + 1];
+            if (last)
+                MDIMG_LAUNCH k_haar_inv<T, T, MODE, true><<<grid, NT, 0, st>>>(ain, p.r_cap, a_pitch, hd, wd, d, skip, l,
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out);
+            else
+                MDIMG_LAUNCH k_haar_inv<T, T, MODE, false><<<grid, NT, 0, st>>>(ain, p.r_cap, a_pitch, hd, wd, d, skip, l,
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out);
+        }
+        cur ^= 1;
+    }
+}
+
+}  // namespace
+
+size_t wavelet_workspace_bytes(int n, int n_sel, int h, int w) {
+    Pyramid p = make_pyramid(h, w);
+    Arena a(nullptr, 0);
+    WaveBufs b;
+    carve(a, n, n_sel, p, b);
+    return a.off;
+}
+
+int wavelet_denoise_run(const float* in, float* out, const Dims& d, int mode_hard,
+                        const double* sigma_in, double sigma_scale, const int* skip,
+                        void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    Pyramid p = make_pyramid(d.h, d.w);
+    Arena a(ws, ws_bytes);
+    WaveBufs b;
+    carve(a, d.n, d.n_sel, p, b);
+    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "wavelet: workspace too small (%zu > %zu)", a.off, ws_bytes);
+    cudaMemsetAsync(b.acc, 0, sizeof(WaveAcc) * d.n_sel, stream);
+    const int want_hist = sigma_in == nullptr;
+    if (want_hist) cudaMemsetAsync(b.l1, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
+
+    // ---- forward ----
+    float* abuf[2] = {b.a0, b.a1};
+    for (int l = 1; l <= p.L; ++l) {
+        const int h0 = p.H[l - 1], w0 = p.W[l - 1];
+        dim3 grid(grid_x((long long)p.H[l] * p.W[l]), d.n_sel);
+        float* aout = abuf[(l - 1) & 1];
+        if (l == 1)
+            MDIMG_LAUNCH k_haar_fwd<true><<<grid, NT, 0, stream>>>(in, (long long)d.h * d.w, h0, w0, d, skip, l, aout, p.a_cap,
+                                                      b.det, p.det_per_slice, p.off[l], b.acc, b.l1, want_hist);
+        else
+            MDIMG_LAUNCH k_haar_fwd<false><<<grid, NT, 0, stream>>>(abuf[l & 1], p.a_cap, h0, w0, d, skip, l, aout, p.a_cap,
+                                                       b.det, p.det_per_slice, p.off[l], b.acc, b.l1, 0);
+    }
+    const float* coarse = abuf[(p.L - 1) & 1];
+
+    // ---- sigma (finest 'dd' band) and thresholds ----
+    if (want_hist) {
+        const int len = p.H[1] * p.W[1];
+        MDIMG_LAUNCH k_wave_ranks<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, len, b.acc, b.ranks);
+        int rc = select_run(b.det + p.off[1] + 2LL * len, p.det_per_slice, len, d, 2, b.ranks, b.l1, b.med,
+                            b.sel_ws, b.sel_ws_bytes, stream, SEL_COMPACT | SEL_ABS);
+        if (rc) return rc;
+    }
+    MDIMG_LAUNCH k_wave_thresholds<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, p, b.acc, b.med, sigma_in, sigma_scale);
+
+    // ---- inverse ----
+    if (mode_hard) run_inverse<float, 2>(p, d, skip, b, coarse, in, out, stream);
+    else if (sigma_in == nullptr) run_inverse<double, 0>(p, d, skip, b, coarse, in, out, stream);
+    else run_inverse<float, 1>(p, d, skip, b, coarse, in, out, stream);
+    return check_launch("wavelet_denoise");
+}
+
+}  // namespace mdimg

@@ -1,0 +1,314 @@
+"""Stack-level operators: one call = one hot-path step over an [N, H, W] CUDA tensor of slices.
+
+PyTorch is the host container only (device memory, streams); every computation goes through the
+C ABI into the hand-written sm_100a kernels.  Per-slice scalars (sigma, min/max, safeguard
+inputs) come back as small device tensors; nothing here touches pixels on the host.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, load_library
+
+_tls = threading.local()
+
+
+def percentile_plan(n: int, qs: Sequence[float] = (5, 25, 75, 95, 90)) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """numpy's ``np.percentile(a, q)`` plan ('linear' method) for a float32 array of ``n``
+    elements: previous index, next index and float32 interpolation weight per q.
+
+    Mirrors numpy >= 2 (``lib/_function_base_impl.py``): ``q / float32(100)``, virtual index
+    ``(n - 1) * q`` in float32, ``floor``; indices at or above ``n - 1`` collapse to the last
+    element (numpy writes -1)."""
+    lo = np.zeros(len(qs), np.int32)
+    hi = np.zeros(len(qs), np.int32)
+    gamma = np.zeros(len(qs), np.float32)
+    for k, q in enumerate(qs):
+        quant = np.true_divide(q, np.float32(100), out=...)
+        virt = np.asanyarray((n - 1) * quant)
+        prev = np.floor(virt)
+        nxt = prev + 1
+        if virt >= n - 1:
+            prev_i, next_i = n - 1, n - 1
+        elif virt < 0:
+            prev_i, next_i = 0, 0
+        else:
+            prev_i, next_i = int(prev), int(nxt)
+        g = np.asanyarray(virt - prev.astype(np.intp), dtype=virt.dtype)
+        lo[k], hi[k], gamma[k] = prev_i, next_i, np.float32(g)
+    return lo, hi, gamma
+
+
+def gaussian_taps(sigma: float, truncate: float = 4.0) -> np.ndarray:
+    """scipy.ndimage ``_gaussian_kernel1d(sigma, 0, radius)``; returns w[0..radius] (centre first)."""
+    radius = int(truncate * float(sigma) + 0.5)
+    sigma2 = sigma * sigma
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / sigma2 * x**2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[radius:], dtype=np.float64)
+
+
+def bilateral_spatial(d: int, sigma_space: float) -> Tuple[int, np.ndarray]:
+    """Effective odd diameter and the float64 spatial weights of the reference's
+    ``_bilateral_filter`` (pipeline/enhancement.py:117-128)."""
+    d = min(int(d), 9)
+    if d % 2 == 0:
+        d += 1
+    r = d // 2
+    yy, xx = np.mgrid[-r : r + 1, -r : r + 1]
+    w = np.exp(-(xx**2 + yy**2) / (2 * sigma_space**2 * d**2))
+    return d, np.ascontiguousarray(w, dtype=np.float64)
+
+
+class StackOps:
+    """Binds the C ABI to torch tensors on one CUDA device.  Thread-safe: the scratch workspace is
+    per thread, and every call runs on the calling thread's current torch stream."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mdimg_b200 requires a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.index is None:
+            self.device = torch.device(f"cuda:{torch.cuda.current_device()}")
+        self.lib = load_library()
+        with torch.cuda.device(self.device):
+            _lib.ensure_device(self.device.index)
+        self.launches = 0     # number of C-ABI compute calls issued (each is >= 1 kernel launch)
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, nbytes: int) -> Tuple[C.c_void_p, int]:
+        key = f"ws_{self.device.index}"
+        buf = getattr(_tls, key, None)
+        if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                # kernels already queued on the stream may still use the old buffer
+                torch.cuda.current_stream(self.device).synchronize()
+            buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=self.device)
+            setattr(_tls, key, buf)
+        return C.c_void_p(buf.data_ptr()), buf.numel()
+
+    def _ws_for(self, op: int, n: int, h: int, w: int, param: int = 0):
+        return self._workspace(self.lib.mdimg_workspace_bytes(op, n, h, w, param))
+
+    def _img(self, t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+        if t.device != self.device:
+            raise ValueError(f"tensor on {t.device}, ops bound to {self.device}")
+        if t.dtype != dtype or t.dim() != 3 or not t.is_contiguous():
+            raise ValueError(f"expected a contiguous [N, H, W] {dtype} tensor, got {tuple(t.shape)} {t.dtype}")
+        return t
+
+    def _sel(self, sel: Optional[torch.Tensor]):
+        if sel is None:
+            return C.c_void_p(0), 0
+        if sel.dtype != torch.int32 or sel.device != self.device or not sel.is_contiguous():
+            raise ValueError("sel must be a contiguous int32 CUDA tensor")
+        return C.c_void_p(sel.data_ptr()), int(sel.numel())
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    def _call(self, fn, *args):
+        with torch.cuda.device(self.device):
+            rc = fn(*args)
+        self.launches += 1
+        check(rc)
+
+    # ---- ingestion --------------------------------------------------------------------------
+    def normalize(self, raw: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """normalize_image per slice (pipeline/dicom_io.py:84-91); uint16 or float32 input."""
+        n, h, w = raw.shape
+        if raw.dtype == torch.uint16 or raw.dtype == torch.int16:
+            # int16 storage is accepted as a uint16 bit pattern container
+            src = self._img(raw, raw.dtype)
+            fn = self.lib.mdimg_normalize_u16
+        else:
+            src = self._img(raw)
+            fn = self.lib.mdimg_normalize_f32
+        if out is None:
+            out = torch.empty((n, h, w), dtype=torch.float32, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_NORMALIZE, n, h, w)
+        self._call(fn, self._ptr(src), self._ptr(out), n, h, w, C.c_void_p(0), 0, ws, wsb, self._stream())
+        return out
+
+    def minmax(self, img: torch.Tensor, sel=None) -> torch.Tensor:
+        n, h, w = self._img(img).shape
+        out = torch.zeros((n, 2), dtype=torch.float32, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_MINMAX, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_minmax_f32, self._ptr(img), n, h, w, sp, ns, self._ptr(out), ws, wsb, self._stream())
+        return out
+
+    # ---- metrics ------------------------------------------------------------------------------
+    def metrics(self, img: torch.Tensor, with_niqe: bool = False, sel=None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[N, 24] float64 rows: the 16 compute_metrics values + mean, edge ratio, NIQE, ..."""
+        n, h, w = self._img(img).shape
+        lo, hi, gamma = percentile_plan(h * w)
+        if out is None:
+            out = torch.full((n, _lib.METRIC_COLS), float("nan"), dtype=torch.float64, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_METRICS, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_metrics, self._ptr(img), n, h, w, sp, ns, 1 if with_niqe else 0,
+                   lo.ctypes.data_as(C.POINTER(C.c_int32)), hi.ctypes.data_as(C.POINTER(C.c_int32)),
+                   gamma.ctypes.data_as(C.POINTER(C.c_float)), self._ptr(out), ws, wsb, self._stream())
+        return out
+
+    def estimate_sigma(self, img: torch.Tensor, sel=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n, h, w = self._img(img).shape
+        if out is None:
+            out = torch.full((n,), float("nan"), dtype=torch.float64, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_SIGMA, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_estimate_sigma, self._ptr(img), n, h, w, sp, ns, self._ptr(out), ws, wsb, self._stream())
+        return out
+
+    def quality(self, img: torch.Tensor, niqe: bool = True, sel=None) -> torch.Tensor:
+        """[N, 2] float64: (edge_ratio, niqe_approx)."""
+        n, h, w = self._img(img).shape
+        out = torch.full((n, 2), float("nan"), dtype=torch.float64, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_QUALITY, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_quality, self._ptr(img), n, h, w, sp, ns, 1 if niqe else 0, self._ptr(out), ws, wsb, self._stream())
+        return out
+
+    def fullref(self, original: torch.Tensor, enhanced: torch.Tensor, sel=None) -> torch.Tensor:
+        """[N, 2] float64: (ssim, psnr)."""
+        n, h, w = self._img(original).shape
+        if tuple(self._img(enhanced).shape) != (n, h, w):
+            raise ValueError("Input images must have the same dimensions.")
+        out = torch.full((n, 2), float("nan"), dtype=torch.float64, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_FULLREF, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_fullref, self._ptr(original), self._ptr(enhanced), n, h, w, sp, ns,
+                   self._ptr(out), ws, wsb, self._stream())
+        return out
+
+    # ---- enhancement steps --------------------------------------------------------------------
+    def wavelet_denoise(self, src, dst, mode: str = "soft", sigma: Optional[torch.Tensor] = None,
+                        sigma_scale: float = 1.0, sel=None):
+        n, h, w = self._img(src).shape
+        self._img(dst)
+        ws, wsb = self._ws_for(_lib.OP_WAVELET, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_wavelet_denoise, self._ptr(src), self._ptr(dst), n, h, w, sp, ns,
+                   1 if mode == "hard" else 0, self._ptr(sigma), float(sigma_scale), C.c_void_p(0),
+                   ws, wsb, self._stream())
+        return dst
+
+    def clahe(self, src, dst, clip_limit: float, kernel_size: int, sel=None) -> torch.Tensor:
+        """Returns the per-slice status tensor (1 = input outside [-1, 1])."""
+        n, h, w = self._img(src).shape
+        self._img(dst)
+        status = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_CLAHE, n, h, w, int(kernel_size))
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_clahe, self._ptr(src), self._ptr(dst), n, h, w, sp, ns,
+                   float(clip_limit), int(kernel_size), self._ptr(status), ws, wsb, self._stream())
+        return status
+
+    def gamma(self, src, dst, gamma: float, assume_nonneg: bool = False, sel=None) -> torch.Tensor:
+        n, h, w = self._img(src).shape
+        self._img(dst)
+        neg = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_GAMMA, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_gamma, self._ptr(src), self._ptr(dst), n, h, w, sp, ns, float(gamma),
+                   1 if assume_nonneg else 0, self._ptr(neg), ws, wsb, self._stream())
+        return neg
+
+    def unsharp(self, src, dst, radius: float, amount: float, assume_nonneg: bool = False, sel=None):
+        n, h, w = self._img(src).shape
+        self._img(dst)
+        taps = gaussian_taps(radius)
+        ws, wsb = self._ws_for(_lib.OP_UNSHARP, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_unsharp, self._ptr(src), self._ptr(dst), n, h, w, sp, ns,
+                   taps.ctypes.data_as(C.POINTER(C.c_double)), len(taps) - 1, float(amount),
+                   1 if assume_nonneg else 0, ws, wsb, self._stream())
+        return dst
+
+    def light_denoise(self, src, dst, strength: float, sel=None) -> torch.Tensor:
+        """Returns per-slice `skipped` flags (sigma < 0.001 left the slice unchanged)."""
+        n, h, w = self._img(src).shape
+        self._img(dst)
+        skipped = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_LIGHT_DENOISE, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_light_denoise, self._ptr(src), self._ptr(dst), n, h, w, sp, ns,
+                   float(strength), self._ptr(skipped), ws, wsb, self._stream())
+        return skipped
+
+    def bilateral(self, src, dst, d: int, sigma_color: float, sigma_space: float, sel=None):
+        n, h, w = self._img(src).shape
+        self._img(dst)
+        deff, spatial = bilateral_spatial(d, sigma_space)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_bilateral, self._ptr(src), self._ptr(dst), n, h, w, sp, ns, deff,
+                   spatial.ctypes.data_as(C.POINTER(C.c_double)), float(sigma_color), self._stream())
+        return dst
+
+    def tv_chambolle(self, src, dst, weight: float, eps: float = 2.0e-4, max_iter: int = 200, sel=None) -> torch.Tensor:
+        """Returns the per-slice number of executed iterations."""
+        n, h, w = self._img(src).shape
+        self._img(dst)
+        iters = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_TV, n, h, w, int(max_iter))
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_tv_chambolle, self._ptr(src), self._ptr(dst), n, h, w, sp, ns,
+                   float(weight), float(eps), int(max_iter), self._ptr(iters), ws, wsb, self._stream())
+        return iters
+
+    def axpby(self, a, b, dst, c0: float, c1: float, clip01: bool = False, sel=None):
+        n, h, w = self._img(a).shape
+        self._img(b)
+        self._img(dst)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_axpby, self._ptr(a), self._ptr(b), self._ptr(dst), n, h, w, sp, ns,
+                   float(c0), float(c1), 1 if clip01 else 0, self._stream())
+        return dst
+
+    def clip01(self, src, dst, sel=None):
+        n, h, w = self._img(src).shape
+        self._img(dst)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_clip01, self._ptr(src), self._ptr(dst), n, h, w, sp, ns, self._stream())
+        return dst
+
+    def copy(self, src, dst, sel=None):
+        n, h, w = self._img(src).shape
+        self._img(dst)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_copy, self._ptr(src), self._ptr(dst), n, h, w, sp, ns, self._stream())
+        return dst
+
+
+_ops_lock = threading.Lock()
+_ops_by_device: dict = {}
+
+
+def get_ops(device=None) -> StackOps:
+    """Process-wide StackOps per device."""
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("mdimg_b200 requires a CUDA device (B200, sm_100a); there is no CPU fallback")
+        device = torch.device(f"cuda:{torch.cuda.current_device()}")
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    with _ops_lock:
+        ops = _ops_by_device.get(key)
+        if ops is None:
+            ops = StackOps(torch.device(f"cuda:{key}"))
+            _ops_by_device[key] = ops
+    return ops

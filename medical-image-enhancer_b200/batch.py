@@ -1,0 +1,174 @@
+"""Stack pipeline: normalise -> enhance (plan) -> metrics + validation for [N, H, W] stacks.
+
+This is the batch form of what the reference's runner does per image
+(``normalize_image`` -> ``apply_enhancements_from_params`` -> ``compute_metrics(enhanced)`` +
+``compute_validation(original, enhanced)``; pipeline/runner.py:80-153, pipeline/tools.py:113-141).
+Slices are independent, so a stack is processed in chunks sized to keep one chunk's working set
+(input, current, scratch, TV state) inside the 126 MB L2: the multi-pass steps (TV iterations,
+radix-select refinements, CLAHE passes) then re-read L2, not HBM.
+
+Results identical to per-slice calls; ``compute_metrics`` of the same image is evaluated once
+per image (the reference recomputes the same values up to four times).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .engine import (MC_EDGE_RATIO, MC_NIQE, METRIC_KEYS, Engine, metrics_dict, objective_score,
+                     validation_dict)
+from .stack import StackOps, get_ops
+
+ROW_COLS = 24
+#: packed per-slice result row: metrics_before[24] | metrics_after[24] | ssim psnr | halo noise over | tv_iters
+PACK_COLS = 2 * ROW_COLS + 2 + 3 + 1
+
+
+@dataclass
+class StackResult:
+    enhanced: Optional[torch.Tensor]        # [N, H, W] float32 on the device (None if not kept)
+    packed: np.ndarray                      # [N, PACK_COLS] float64 on the host
+    labels: List[List[str]]
+
+    @property
+    def rows_before(self) -> np.ndarray:
+        return self.packed[:, :ROW_COLS]
+
+    @property
+    def rows_after(self) -> np.ndarray:
+        return self.packed[:, ROW_COLS:2 * ROW_COLS]
+
+    def metrics_after(self, i: int) -> Dict[str, float]:
+        return metrics_dict(self.rows_after[i])
+
+    def metrics_before(self, i: int) -> Dict[str, float]:
+        return metrics_dict(self.rows_before[i])
+
+    def validation(self, i: int) -> Dict[str, object]:
+        rb, ra = self.rows_before[i], self.rows_after[i]
+        ssim, psnr = self.packed[i, 2 * ROW_COLS], self.packed[i, 2 * ROW_COLS + 1]
+        return validation_dict(metrics_dict(rb), metrics_dict(ra), float(ssim), float(psnr),
+                               float(rb[MC_NIQE]), float(ra[MC_NIQE]), float(ra[MC_EDGE_RATIO]))
+
+    def score(self, i: int):
+        return objective_score(self.validation(i))
+
+    def scores(self) -> np.ndarray:
+        return np.array([self.score(i)[0] for i in range(self.packed.shape[0])])
+
+
+def default_chunk(h: int, w: int, l2_bytes: int = 126 << 20) -> int:
+    """Slices per chunk so that ~9 float32 images per slice (input, current, scratch, 4 planes of TV
+    state, |grad| buffer, pyramid) stay L2-resident; never below 4 slices."""
+    per_slice = 9 * 4 * h * w
+    return int(max(4, min(1024, (l2_bytes * 3 // 4) // max(per_slice, 1))))
+
+
+def process_chunk(ops: StackOps, raw: torch.Tensor, plan, keep_enhanced: bool = True):
+    """One chunk on the current stream.  Returns (enhanced | None, packed device rows, labels)."""
+    eng = Engine(ops)
+    n = raw.shape[0]
+    x = ops.normalize(raw)
+    rows_b = ops.metrics(x, with_niqe=True)
+    res = eng.enhance_from_params(
+        x, plan, sigma_before=rows_b[:, 0].contiguous(),
+        quality_before=rows_b[:, MC_EDGE_RATIO:MC_NIQE + 1].contiguous())
+    rows_a = ops.metrics(res.image, with_niqe=True)
+    fr = ops.fullref(x, res.image)
+    packed = torch.empty((n, PACK_COLS), dtype=torch.float64, device=ops.device)
+    packed[:, :ROW_COLS] = rows_b
+    packed[:, ROW_COLS:2 * ROW_COLS] = rows_a
+    packed[:, 2 * ROW_COLS:2 * ROW_COLS + 2] = fr
+    flags = np.stack([res.halo, res.noise_guard, res.over_processed], axis=1).astype(np.float64)
+    packed[:, 2 * ROW_COLS + 2:2 * ROW_COLS + 5] = torch.from_numpy(flags).to(ops.device)
+    if res.tv_iterations is not None:
+        packed[:, 2 * ROW_COLS + 5] = torch.from_numpy(res.tv_iterations.astype(np.float64)).to(ops.device)
+    else:
+        packed[:, 2 * ROW_COLS + 5] = 0
+    return (res.image if keep_enhanced else None), packed, res.labels
+
+
+def process_stack(raw: torch.Tensor, plan, chunk: Optional[int] = None, keep_enhanced: bool = True,
+                  ops: Optional[StackOps] = None) -> StackResult:
+    """Device-resident stack (uint16 bit pattern in an int16/uint16 tensor, or float32) ->
+    enhanced stack + per-slice metric / validation rows."""
+    ops = ops or get_ops(raw.device)
+    n, h, w = raw.shape
+    chunk = chunk or default_chunk(h, w)
+    enhanced = torch.empty((n, h, w), dtype=torch.float32, device=ops.device) if keep_enhanced else None
+    packed_dev = torch.empty((n, PACK_COLS), dtype=torch.float64, device=ops.device)
+    labels: List[List[str]] = []
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        enh, packed, lab = process_chunk(ops, raw[a:b], plan, keep_enhanced)
+        if keep_enhanced:
+            enhanced[a:b] = enh
+        packed_dev[a:b] = packed
+        labels.extend(lab)
+    return StackResult(enhanced=enhanced, packed=packed_dev.cpu().numpy(), labels=labels)
+
+
+def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
+                       out_host: Optional[np.ndarray] = None, ops: Optional[StackOps] = None,
+                       pinned_in: Optional[torch.Tensor] = None, pinned_out: Optional[torch.Tensor] = None):
+    """End-to-end form with HOST buffers: per chunk, host->device copy of the raw slices, the whole
+    pipeline on the GPU, device->host copy of the enhanced slices and of the result rows.
+    Copies of chunk k+1 / k-1 overlap the compute of chunk k on side streams.
+
+    raw_host: [N, H, W] uint16 or float32 numpy array (ideally backed by pinned memory).
+    Returns (enhanced float32 host array, StackResult without device pixels)."""
+    ops = ops or get_ops()
+    n, h, w = raw_host.shape
+    chunk = chunk or default_chunk(h, w)
+    dev = ops.device
+    if raw_host.dtype == np.uint16:
+        src_t = pinned_in if pinned_in is not None else torch.from_numpy(raw_host.view(np.int16))
+    else:
+        src_t = pinned_in if pinned_in is not None else torch.from_numpy(np.ascontiguousarray(raw_host, np.float32))
+    if out_host is None:
+        out_t = pinned_out if pinned_out is not None else torch.empty((n, h, w), dtype=torch.float32, pin_memory=True)
+    else:
+        out_t = torch.from_numpy(out_host)
+    packed_host = torch.empty((n, PACK_COLS), dtype=torch.float64, pin_memory=True)
+    main = torch.cuda.current_stream(dev)
+    copy_in = torch.cuda.Stream(dev)
+    copy_out = torch.cuda.Stream(dev)
+    labels: List[List[str]] = []
+    spans = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
+    staged = {}
+
+    def stage(i):
+        a, b = spans[i]
+        with torch.cuda.stream(copy_in):
+            t = src_t[a:b].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_in)
+        staged[i] = (t, ev)
+
+    if spans:
+        stage(0)
+    pending = []
+    for i, (a, b) in enumerate(spans):
+        if i + 1 < len(spans):
+            stage(i + 1)
+        raw_d, ev = staged.pop(i)
+        main.wait_event(ev)
+        raw_d.record_stream(main)
+        enh, packed, lab = process_chunk(ops, raw_d, plan, True)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(copy_out):
+            copy_out.wait_event(done)
+            out_t[a:b].copy_(enh, non_blocking=True)
+            packed_host[a:b].copy_(packed, non_blocking=True)
+            enh.record_stream(copy_out)
+            packed.record_stream(copy_out)
+        labels.extend(lab)
+    copy_out.synchronize()
+    main.synchronize()
+    res = StackResult(enhanced=None, packed=packed_host.numpy().copy(), labels=labels)
+    return out_t.numpy(), res

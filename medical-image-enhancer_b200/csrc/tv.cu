@@ -219,7 +219,7 @@ int tv_chambolle_run(const float* in, float* out, const Dims& d, double weight, 
         MDIMG_LAUNCH k_tv_iter<<<grid, NT, 0, stream>>>(in, d, i, pin, pout, p_stride, b.energy, max_iter, b.state,
                                            w, tau_over_w, epsf);
         launched = i + 1;
-        if (i >= 2 && (i % POLL) == 0 && i + 1 < max_iter) {
+        if (eps > 0.0 && i >= 2 && (i % POLL) == 0 && i + 1 < max_iter) {
             cudaMemsetAsync(b.live, 0, sizeof(int), stream);
             MDIMG_LAUNCH k_tv_count<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d.n_sel, b.state, b.live);
             cudaMemcpyAsync(live_host, b.live, sizeof(int), cudaMemcpyDeviceToHost, stream);

@@ -1,0 +1,228 @@
+"""The reference's own hot-path tests (tests/test_metrics.py, tests/test_pipeline.py,
+tests/test_detection.py of Hiresh444/medical-image-enhancer), restated against the drop-in
+modules, plus end-to-end parity of both enhancement entry points with the oracle."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import ref_enhancement as oenh
+from oracle import ref_metrics as omet
+
+pytestmark = pytest.mark.gpu
+
+LSB16 = 1.0 / 65535
+EXPECTED_KEYS = {
+    "sigma", "lap_var", "std", "pct_low", "pct_high", "entropy", "edge_density", "gradient_mag_mean",
+    "gradient_mag_std", "snr_proxy", "cnr_proxy", "laplacian_energy", "histogram_spread",
+    "local_contrast_std", "gradient_strength", "gradient_entropy",
+}
+
+
+@pytest.fixture(scope="module")
+def api(ops):
+    from mdimg_b200.pipeline import dicom_io, enhancement, metrics, schemas
+    return type("Api", (), {"metrics": metrics, "enhancement": enhancement, "schemas": schemas,
+                            "dicom_io": dicom_io})
+
+
+# ---- tests/test_metrics.py -------------------------------------------------------------------
+def test_returns_all_16_keys(api, synthetic_image_clean):
+    m = api.metrics.compute_metrics(synthetic_image_clean)
+    assert set(m) == EXPECTED_KEYS and len(m) == 16
+    assert all(isinstance(v, float) and np.isfinite(v) for v in m.values())
+
+
+def test_entropy_snr_ordering(api, synthetic_image_clean, synthetic_image_noisy):
+    clean = api.metrics.compute_metrics(synthetic_image_clean)
+    noisy = api.metrics.compute_metrics(synthetic_image_noisy)
+    assert clean["entropy"] >= 0 and clean["snr_proxy"] >= 0
+    assert clean["snr_proxy"] > noisy["snr_proxy"]
+    assert noisy["sigma"] > 0.08
+
+
+def test_validation_identical_images(api, synthetic_image_clean):
+    v = api.metrics.compute_validation(synthetic_image_clean, synthetic_image_clean)
+    for key in ("entropy_change", "snr_change", "cnr_change", "edge_ratio", "laplacian_energy_before",
+                "laplacian_energy_after", "ssim", "psnr", "niqe_before", "metrics_before", "metrics_after"):
+        assert key in v
+    assert len(v) == 38
+    assert v["passes"] is True
+    assert v["ssim"] == pytest.approx(1.0)
+
+
+def test_objective_score_types(api, synthetic_image_clean):
+    v = api.metrics.compute_validation(synthetic_image_clean, synthetic_image_clean)
+    score, breakdown = api.metrics.compute_objective_score(v)
+    assert isinstance(score, float) and isinstance(breakdown, dict)
+
+
+def test_edge_ratio_range(api, synthetic_image_clean):
+    er = api.metrics.compute_edge_ratio(synthetic_image_clean)
+    assert isinstance(er, float) and 0 <= er <= 1.0 or er == pytest.approx(omet.compute_edge_ratio(synthetic_image_clean), rel=1e-5)
+
+
+# ---- tests/test_detection.py -------------------------------------------------------------------
+def test_normalize_image(api):
+    out = api.dicom_io.normalize_image(np.array([[10, 20], [30, 40]], dtype=np.float32))
+    assert out.dtype == np.float32
+    assert float(out.min()) == pytest.approx(0.0) and float(out.max()) == pytest.approx(1.0)
+    assert not api.dicom_io.normalize_image(np.full((8, 8), 7, np.float32)).any()
+    u16 = np.arange(64, dtype=np.uint16).reshape(8, 8) * 50
+    np.testing.assert_array_equal(api.dicom_io.normalize_image(u16), omet.normalize_image(u16))
+
+
+def test_detect_issues_on_fixtures(api, synthetic_image_noisy, synthetic_image_low_contrast):
+    assert "noise" in api.metrics.detect_issues(api.metrics.compute_metrics(synthetic_image_noisy))
+    assert "low_contrast" in api.metrics.detect_issues(api.metrics.compute_metrics(synthetic_image_low_contrast))
+
+
+# ---- tests/test_pipeline.py -------------------------------------------------------------------
+def test_apply_enhancements_returns_valid_image(api, synthetic_image_noisy):
+    before = synthetic_image_noisy.copy()
+    enhanced, ops_ = api.enhancement.apply_enhancements(synthetic_image_noisy, ["noise"])
+    assert enhanced.shape == synthetic_image_noisy.shape and enhanced.dtype == np.float32
+    assert float(enhanced.min()) >= 0.0 and float(enhanced.max()) <= 1.0
+    assert len(ops_) > 0
+    np.testing.assert_array_equal(synthetic_image_noisy, before)      # input never mutated
+
+
+def test_no_ops_when_no_issues(api, synthetic_image_clean):
+    enhanced, ops_ = api.enhancement.apply_enhancements(synthetic_image_clean, [])
+    assert ops_ == []
+    np.testing.assert_array_equal(enhanced, synthetic_image_clean)
+
+
+def _plan(api, **kw):
+    params = kw.pop("params", {})
+    return api.schemas.EnhancementPlan(params=api.schemas.EnhancementParams(**params), **kw)
+
+
+def test_basic_plan(api, synthetic_image_noisy):
+    plan = _plan(api, recommended_ops=["denoise", "clahe", "gamma", "unsharp"],
+                 params=dict(clahe_clip_limit=0.02, clahe_tile_size=16, gamma=0.95, unsharp_radius=0.8,
+                             unsharp_amount=0.5, denoise_mode="soft", post_denoise_strength=0.2))
+    enhanced, ops_ = api.enhancement.apply_enhancements_from_params(synthetic_image_noisy, plan)
+    assert enhanced.shape == (64, 64) and enhanced.dtype == np.float32
+    assert 0.0 <= float(enhanced.min()) and float(enhanced.max()) <= 1.0 and len(ops_) > 0
+    ref, ref_ops = oenh.apply_enhancements_from_params(synthetic_image_noisy, plan)
+    assert ops_ == ref_ops
+    assert float((np.abs(enhanced - ref) > LSB16).mean()) < 0.01
+
+
+def test_empty_ops(api, synthetic_image_clean):
+    enhanced, ops_ = api.enhancement.apply_enhancements_from_params(
+        synthetic_image_clean, _plan(api, recommended_ops=[], stop_reason="No issues."))
+    assert ops_ == []
+
+
+def test_parameter_clamping(api, synthetic_image_noisy):
+    plan = _plan(api, recommended_ops=["clahe", "unsharp"],
+                 params=dict(clahe_clip_limit=999.0, unsharp_amount=-5.0))
+    enhanced, ops_ = api.enhancement.apply_enhancements_from_params(synthetic_image_noisy, plan)
+    assert enhanced.shape == synthetic_image_noisy.shape and len(ops_) >= 1
+    assert "CLAHE (clip=0.0800, tile=16)" in ops_ and any(o.startswith("Unsharp mask (r=0.80, a=0.03)") for o in ops_)
+
+
+def test_invalid_denoise_mode_defaults_to_soft(api, synthetic_image_noisy):
+    plan = _plan(api, recommended_ops=["denoise"], params=dict(denoise_mode="INVALID"))
+    _, ops_ = api.enhancement.apply_enhancements_from_params(synthetic_image_noisy, plan)
+    assert any("soft" in op for op in ops_)
+
+
+def test_validation_enhanced_vs_original(api, synthetic_image_noisy):
+    enhanced, _ = api.enhancement.apply_enhancements(synthetic_image_noisy, ["noise"])
+    v = api.metrics.compute_validation(synthetic_image_noisy, enhanced)
+    assert isinstance(v["passes"], bool) and "niqe_before" in v
+    ref = omet.compute_validation(synthetic_image_noisy, enhanced)
+    for key in ("ssim", "psnr", "niqe_before", "niqe_after", "contrast_gain", "sharpness_gain",
+                "quality_improvement", "edge_ratio", "entropy_change", "snr_change"):
+        assert v[key] == pytest.approx(ref[key], rel=1e-5, abs=1e-7), key
+    for key in ("passes", "meets_ssim", "meets_psnr", "meets_improvement", "niqe_improved"):
+        assert v[key] == ref[key], key
+    assert api.metrics.compute_objective_score(v)[0] == pytest.approx(omet.compute_objective_score(ref)[0], abs=2e-4)
+
+
+def test_deterministic_agent_chain(api, synthetic_image_noisy):
+    """QualityDetection -> Recommendation -> Enhancement -> Validation (pipeline/core_agents.py:61-161)
+    expressed with the drop-in functions."""
+    m = api.metrics.compute_metrics(synthetic_image_noisy)
+    issues = api.metrics.detect_issues(m)
+    assert issues == omet.detect_issues(omet.compute_metrics(synthetic_image_noisy))
+    enhanced, applied = api.enhancement.apply_enhancements(synthetic_image_noisy, issues)
+    ref_img, ref_applied = oenh.apply_enhancements(synthetic_image_noisy, issues)
+    assert applied == ref_applied
+    assert np.abs(enhanced - ref_img).max() <= LSB16
+    v = api.metrics.compute_validation(synthetic_image_noisy, enhanced)
+    status = "PASS" if v["passes"] else ("WARN" if v["quality_improvement"] > 0 else "FAIL")
+    assert status in ("PASS", "WARN", "FAIL")
+
+
+# ---- helper functions of enhancement.py ----------------------------------------------------------
+def test_private_helpers_mirror_the_reference(api, synthetic_image_noisy, synthetic_image_clean):
+    e = api.enhancement
+    assert e._check_halo(synthetic_image_noisy) == oenh.halo_detected(synthetic_image_noisy)
+    assert e._check_noise_amplification(synthetic_image_clean, synthetic_image_noisy) is True
+    assert e._check_noise_amplification(synthetic_image_noisy, synthetic_image_clean) is False
+    assert e._check_over_processing(synthetic_image_clean, synthetic_image_noisy) == \
+        oenh.over_processed(synthetic_image_clean, synthetic_image_noisy)
+    assert e._bilateral_filter(synthetic_image_clean, d=0) is synthetic_image_clean
+    flat = np.full((64, 64), 0.25, np.float32)
+    assert e._light_denoise(flat + 0) is not None
+
+
+# ---- full plans vs the oracle ----------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["noisy64", "ct512", "odd94x141"])
+def test_p_full_matches_the_oracle(api, images, synth, name):
+    im = images[name]
+    got, labels = api.enhancement.apply_enhancements_from_params(im, synth.plan_full())
+    ref, ref_labels = oenh.apply_enhancements_from_params(im, synth.plan_full())
+    assert labels == ref_labels
+    d = np.abs(got.astype(np.float64) - ref)
+    # Tolerance: <= 1 LSB of a 16-bit export on >= 99% of pixels.  A 1-ulp difference entering
+    # CLAHE (BayesShrink thresholds summed in float64 here, float32-pairwise in numpy) can move a
+    # pixel across a gray-bin edge, which shifts one contextual region's LUT by 1/k^2.
+    assert float((d > LSB16).mean()) < 0.01
+    assert d.max() < 5e-3
+
+
+@pytest.mark.parametrize("name", ["cr600", "ct512"])
+def test_p_cr_matches_the_oracle(api, images, synth, name):
+    im = images[name]
+    got, labels = api.enhancement.apply_enhancements_from_params(im, synth.plan_cr())
+    ref, ref_labels = oenh.apply_enhancements_from_params(im, synth.plan_cr())
+    assert labels == ref_labels
+    assert np.abs(got - ref).max() <= LSB16
+
+
+@pytest.mark.parametrize("issues", [["noise"], ["blur"], ["low_contrast", "clipping_low"],
+                                    ["noise", "blur", "clipping_high"]])
+@pytest.mark.parametrize("name", ["noisy64", "ct512"])
+def test_issue_driven_enhancement_matches_the_oracle(api, images, issues, name):
+    im = images[name]
+    got, labels = api.enhancement.apply_enhancements(im, issues)
+    ref, ref_labels = oenh.apply_enhancements(im, issues)
+    assert labels == ref_labels
+    assert np.abs(got - ref).max() <= LSB16
+
+
+def test_stack_pipeline_matches_per_slice_calls(ops, synth):
+    import torch
+    from mdimg_b200.batch import process_stack, process_stack_host
+    raw = np.stack([synth.ct_slice(1000 + z, z / 6, size=256) for z in range(6)])
+    plan = synth.plan_full()
+    res = process_stack(torch.from_numpy(raw.view(np.int16)).to(ops.device), plan, chunk=4)
+    out_h, res_h = process_stack_host(raw, plan, chunk=4, ops=ops)
+    np.testing.assert_array_equal(res.enhanced.cpu().numpy(), out_h)
+    np.testing.assert_array_equal(res.packed, res_h.packed)
+    for z in (0, 5):
+        x = omet.normalize_image(raw[z])
+        ref, ref_labels = oenh.apply_enhancements_from_params(x, plan)
+        assert res.labels[z] == ref_labels
+        assert float((np.abs(out_h[z].astype(np.float64) - ref) > LSB16).mean()) < 0.01
+        v = res.validation(z)
+        refv = omet.compute_validation(x, out_h[z])
+        assert v["ssim"] == pytest.approx(refv["ssim"], rel=1e-6)
+        assert v["metrics_after"]["entropy"] == pytest.approx(refv["metrics_after"]["entropy"], rel=1e-9)
+        assert isinstance(res.score(z)[0], float)

@@ -1,0 +1,159 @@
+"""Host-side logic of the product path (no GPU): percentile plans, filter taps, parameter
+clamping, labels, validation / scoring arithmetic and the multi-rank sharding + gather (gloo,
+world_size 2)."""
+
+from __future__ import annotations
+
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+from scipy import ndimage as ndi
+
+from mdimg_b200 import engine
+from mdimg_b200.shard import gather_rows, slice_range
+from mdimg_b200.stack import bilateral_spatial, gaussian_taps, percentile_plan
+from oracle import ref_enhancement as oenh
+from oracle import ref_metrics as omet
+
+
+def _lerp32(a, b, t):
+    a, b, t = np.float32(a), np.float32(b), np.float32(t)
+    d = b - a
+    r = a + d * t
+    if t >= 0.5:
+        r = b - d * (np.float32(1) - t)
+    return r
+
+
+@pytest.mark.parametrize("n", [7, 64 * 64, 512 * 512, 3000 * 3000, 94 * 141])
+def test_percentile_plan_reproduces_numpy_bit_for_bit(n):
+    x = np.random.default_rng(n).random(n).astype(np.float32)
+    xs = np.sort(x)
+    lo, hi, g = percentile_plan(n)
+    for k, q in enumerate((5, 25, 75, 95, 90)):
+        assert _lerp32(xs[lo[k]], xs[hi[k]], g[k]) == np.percentile(x, q)
+
+
+def test_gaussian_taps_are_scipys():
+    for sigma in (0.2, 0.8, 1.7, 3.0):
+        taps = gaussian_taps(sigma)
+        r = len(taps) - 1
+        assert r == int(4 * sigma + 0.5)
+        imp = np.zeros(4 * r + 3)
+        imp[2 * r + 1] = 1.0
+        ref = ndi.gaussian_filter1d(imp, sigma, truncate=4.0)
+        np.testing.assert_array_equal(ref[2 * r + 1: 3 * r + 2], taps)
+
+
+def test_bilateral_spatial_matches_reference_formula():
+    for d, want in ((5, 5), (4, 5), (13, 9), (9, 9), (1, 1), (2, 3)):
+        deff, w = bilateral_spatial(d, 0.05)
+        assert deff == want and w.shape == (want, want) and w.dtype == np.float64
+        r = want // 2
+        assert w[r, r] == 1.0
+        assert w[0, 0] == np.exp(-(2 * r * r) / (2 * 0.05**2 * want**2))
+
+
+def test_param_bounds_contract():
+    from mdimg_b200.pipeline.schemas import PARAM_BOUNDS, EnhancementParams
+    assert set(PARAM_BOUNDS) == {
+        "clahe_clip_limit", "clahe_tile_size", "gamma", "unsharp_radius", "unsharp_amount",
+        "post_denoise_strength", "bilateral_d", "bilateral_sigma_color", "bilateral_sigma_space",
+        "tv_denoise_weight"}
+    assert all(lo < hi for lo, hi in PARAM_BOUNDS.values())
+    assert PARAM_BOUNDS == oenh.PARAM_BOUNDS
+    p = EnhancementParams()
+    assert (p.clahe_clip_limit, p.clahe_tile_size, p.gamma, p.unsharp_radius, p.unsharp_amount,
+            p.denoise_mode, p.post_denoise_strength, p.bilateral_d, p.tv_denoise_weight) == \
+        (0.015, 16, 1.0, 0.8, 0.5, "soft", 0.3, 0, 0.0)
+
+
+def test_clamping_and_labels_follow_the_reference():
+    wild = SimpleNamespace(clahe_clip_limit=999.0, clahe_tile_size=1000, gamma=0.1, unsharp_radius=9.0,
+                           unsharp_amount=-5.0, denoise_mode="INVALID", post_denoise_strength=2.0,
+                           bilateral_d=40, bilateral_sigma_color=5.0, bilateral_sigma_space=0.0,
+                           tv_denoise_weight=3.0)
+    q = engine.ClampedParams.from_params(wild)
+    ref = oenh.clamp_plan_params(wild)
+    assert (q.clip_limit, q.tile_size, q.gamma, q.u_radius, q.u_amount, q.dn_mode, q.post_str,
+            q.bilateral_d, q.bilateral_sc, q.bilateral_ss, q.tv_weight) == \
+        (ref["clip_limit"], ref["tile_size"], ref["gamma"], ref["u_radius"], ref["u_amount"],
+         ref["dn_mode"], ref["post_str"], ref["bilateral_d"], ref["bilateral_sc"], ref["bilateral_ss"],
+         ref["tv_weight"])
+    assert q.dn_mode == "soft" and q.clip_limit == 0.08 and q.u_amount == 0.03 and q.bilateral_d == 13
+    table = oenh._step_table(ref, ref["u_amount"])
+    for name in engine._STEP_ORDER:
+        assert engine.Engine._label(name, q) == table[name][2]
+        assert engine.Engine._enabled(name, q) == table[name][0]
+
+
+def test_validation_and_score_arithmetic_match_the_oracle(synthetic_image_noisy):
+    x = synthetic_image_noisy
+    y, _ = oenh.apply_enhancements(x, ["noise"])
+    ref = omet.compute_validation(x, y)
+    got = engine.validation_dict(ref["metrics_before"], ref["metrics_after"], ref["ssim"], ref["psnr"],
+                                 ref["niqe_before"], ref["niqe_after"], ref["edge_ratio"])
+    assert list(got) == list(ref)
+    assert len(got) == 38 and got["passes"] is ref["passes"]
+    for k in ref:
+        assert got[k] == ref[k], k
+    assert engine.objective_score(got) == omet.compute_objective_score(ref)
+    assert engine.METRIC_KEYS == omet.METRIC_KEYS and engine.THRESHOLDS == omet.THRESHOLDS
+
+
+def test_detect_issues_thresholds():
+    from mdimg_b200.pipeline.metrics import detect_issues
+    ok = {"sigma": 0.03, "lap_var": 0.01, "std": 0.25, "pct_low": 0.005, "pct_high": 0.005}
+    bad = {"sigma": 0.15, "lap_var": 0.0005, "std": 0.05, "pct_low": 0.05, "pct_high": 0.05}
+    assert detect_issues(ok) == []
+    assert detect_issues(bad) == ["noise", "blur", "low_contrast", "clipping_low", "clipping_high"]
+    assert detect_issues(bad) == omet.detect_issues(bad)
+
+
+def test_slice_range_partitions():
+    for n in (0, 1, 7, 64, 1024, 8192):
+        for world in (1, 2, 3, 8):
+            spans = [slice_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert slice_range(8192, 3, 8) == (3072, 4096)
+
+
+def _gloo_worker(rank, world, n_total, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = slice_range(n_total, rank, world)
+    rows = torch.arange(a, b, dtype=torch.float64)[:, None] * torch.ones((1, 5), dtype=torch.float64) + rank / 10
+    out = gather_rows(rows, n_total)
+    q.put((rank, out.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 7])
+def test_gather_rows_gloo_world2(n_total):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + n_total
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, n_total, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a0, b0 = slice_range(n_total, 0, 2)
+    for r in range(2):
+        out = results[r]
+        assert out.shape == (n_total, 5)
+        want = np.arange(n_total, dtype=np.float64)[:, None] * np.ones((1, 5))
+        want[b0:] += 0.1
+        np.testing.assert_allclose(out, want)

@@ -287,7 +287,7 @@ def run_gpu(args) -> None:
         per_launch_ms = (t_long - t_short) / 40.0
         bytes_per_launch = 20.0 * chunk * H * W
         achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9
-        tv_iters = last.packed[:, -1]
+        tv_iters = last.tv_iterations
         roof = {"bound": "hbm", "kernel": "k_tv_iter", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,

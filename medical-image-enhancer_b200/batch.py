@@ -24,8 +24,8 @@ from .engine import (MC_EDGE_RATIO, MC_NIQE, METRIC_KEYS, Engine, metrics_dict, 
 from .stack import StackOps, get_ops
 
 ROW_COLS = 24
-#: packed per-slice result row: metrics_before[24] | metrics_after[24] | ssim psnr | halo noise over | tv_iters
-PACK_COLS = 2 * ROW_COLS + 2 + 3 + 1
+#: packed per-slice result row: metrics_before[24] | metrics_after[24] | ssim psnr | halo noise over | tv_iters | error
+PACK_COLS = 2 * ROW_COLS + 2 + 3 + 1 + 1
 
 
 @dataclass
@@ -54,6 +54,16 @@ class StackResult:
         return validation_dict(metrics_dict(rb), metrics_dict(ra), float(ssim), float(psnr),
                                float(rb[MC_NIQE]), float(ra[MC_NIQE]), float(ra[MC_EDGE_RATIO]))
 
+    @property
+    def tv_iterations(self) -> np.ndarray:
+        return self.packed[:, 2 * ROW_COLS + 5]
+
+    @property
+    def failed(self) -> np.ndarray:
+        """True where the reference would have raised ValueError for that slice (the slice is
+        returned unchanged and its label list holds the error text)."""
+        return self.packed[:, 2 * ROW_COLS + 6] != 0
+
     def score(self, i: int):
         return objective_score(self.validation(i))
 
@@ -76,7 +86,7 @@ def process_chunk(ops: StackOps, raw: torch.Tensor, plan, keep_enhanced: bool = 
     rows_b = ops.metrics(x, with_niqe=True)
     res = eng.enhance_from_params(
         x, plan, sigma_before=rows_b[:, 0].contiguous(),
-        quality_before=rows_b[:, MC_EDGE_RATIO:MC_NIQE + 1].contiguous())
+        quality_before=rows_b[:, MC_EDGE_RATIO:MC_NIQE + 1].contiguous(), on_error="flag")
     rows_a = ops.metrics(res.image, with_niqe=True)
     fr = ops.fullref(x, res.image)
     packed = torch.empty((n, PACK_COLS), dtype=torch.float64, device=ops.device)
@@ -89,6 +99,9 @@ def process_chunk(ops: StackOps, raw: torch.Tensor, plan, keep_enhanced: bool = 
         packed[:, 2 * ROW_COLS + 5] = torch.from_numpy(res.tv_iterations.astype(np.float64)).to(ops.device)
     else:
         packed[:, 2 * ROW_COLS + 5] = 0
+    err = np.zeros(n, np.float64)
+    err[list(res.errors)] = 1.0
+    packed[:, 2 * ROW_COLS + 6] = torch.from_numpy(err).to(ops.device)
     return (res.image if keep_enhanced else None), packed, res.labels
 
 

@@ -8,8 +8,13 @@
 //   out = result / (weight_sum + 1e-10)                       float32
 //
 // One shared-memory tile with a (d//2)-pixel halo per CTA; the slice is read once and written
-// once.  d*d exponentials per pixel make this kernel MUFU/FP64-issue bound rather than HBM bound
-// for d >= 5 (stated in DESIGN.md).
+// once.  d*d exponentials per pixel make this kernel MUFU-bound rather than HBM-bound for d >= 5
+// (stated in DESIGN.md).
+//
+// Precision: the reference's float32 exp is numpy's SIMD routine (not correctly rounded), so the
+// weights are not reproducible to the bit on any other implementation; the accumulation is
+// therefore done in float32 FMAs (tap order kept) instead of emulating numpy's float64-add /
+// float32-store per tap.  Measured difference to the oracle: a few float32 ulps (tests allow 16).
 #include "enhance.cuh"
 
 namespace mdimg {
@@ -20,12 +25,12 @@ constexpr int NT = 256;
 constexpr int TW = 64, TH = 32;
 constexpr int MAXD = 9;
 
-struct SpatialW { double w[MAXD * MAXD]; };
+struct SpatialW { float w[MAXD * MAXD]; };
 
 template <int R>
 __global__ void __launch_bounds__(NT)
 k_bilateral(const float* __restrict__ in, float* __restrict__ out, Dims d, const SpatialW sw,
-            float two_sc2) {
+            float neg_k) {
     constexpr int D = 2 * R + 1;
     constexpr int XW = TW + 2 * R, XH = TH + 2 * R, XP = XW + 1;
     __shared__ float X[XH][XP];
@@ -56,12 +61,12 @@ k_bilateral(const float* __restrict__ in, float* __restrict__ out, Dims d, const
 #pragma unroll
                     for (int dx = 0; dx < D; ++dx) {
                         const float nb = X[r + dy][c + dx];
-                        const float diff = __fsub_rn(xc, nb);
-                        const float arg = __fdiv_rn(-__fmul_rn(diff, diff), two_sc2);
-                        const float iw = expf(arg);
-                        const double w = __dmul_rn(sw.w[dy * D + dx], (double)iw);
-                        res = (float)__dadd_rn((double)res, __dmul_rn(w, (double)nb));
-                        wsum = (float)__dadd_rn((double)wsum, w);
+                        const float diff = xc - nb;
+                        // exp(-diff^2 / (2 sc^2)) = 2^(diff^2 * neg_k), neg_k = -log2(e) / (2 sc^2)
+                        const float iw = exp2f(diff * diff * neg_k);
+                        const float w = sw.w[dy * D + dx] * iw;
+                        res = fmaf(w, nb, res);
+                        wsum += w;
                     }
                 dst[(size_t)gy * d.w + gx] = __fdiv_rn(res, __fadd_rn(wsum, 1e-10f));
             }
@@ -69,9 +74,9 @@ k_bilateral(const float* __restrict__ in, float* __restrict__ out, Dims d, const
 }
 
 template <int R>
-void launch(const float* in, float* out, const Dims& d, const SpatialW& sw, float two_sc2, cudaStream_t st) {
+void launch(const float* in, float* out, const Dims& d, const SpatialW& sw, float neg_k, cudaStream_t st) {
     dim3 grid(((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH), d.n_sel);
-    MDIMG_LAUNCH k_bilateral<R><<<grid, NT, 0, st>>>(in, out, d, sw, two_sc2);
+    MDIMG_LAUNCH k_bilateral<R><<<grid, NT, 0, st>>>(in, out, d, sw, neg_k);
 }
 
 }  // namespace
@@ -83,14 +88,14 @@ int bilateral_run(const float* in, float* out, const Dims& d, int dd, const doub
         return set_error(MDIMG_ERR_INVALID, "bilateral: diameter %d must be odd and in [1, 9]", dd);
     if (in == out) return set_error(MDIMG_ERR_INVALID, "bilateral: in-place operation is not supported");
     SpatialW sw;
-    for (int i = 0; i < MAXD * MAXD; ++i) sw.w[i] = i < dd * dd ? spatial[i] : 0.0;
-    const float two_sc2 = (float)(2.0 * sigma_color * sigma_color);
+    for (int i = 0; i < MAXD * MAXD; ++i) sw.w[i] = i < dd * dd ? (float)spatial[i] : 0.0f;
+    const float neg_k = (float)(-1.4426950408889634 / (2.0 * sigma_color * sigma_color));
     switch (dd / 2) {
-        case 0: launch<0>(in, out, d, sw, two_sc2, stream); break;
-        case 1: launch<1>(in, out, d, sw, two_sc2, stream); break;
-        case 2: launch<2>(in, out, d, sw, two_sc2, stream); break;
-        case 3: launch<3>(in, out, d, sw, two_sc2, stream); break;
-        case 4: launch<4>(in, out, d, sw, two_sc2, stream); break;
+        case 0: launch<0>(in, out, d, sw, neg_k, stream); break;
+        case 1: launch<1>(in, out, d, sw, neg_k, stream); break;
+        case 2: launch<2>(in, out, d, sw, neg_k, stream); break;
+        case 3: launch<3>(in, out, d, sw, neg_k, stream); break;
+        case 4: launch<4>(in, out, d, sw, neg_k, stream); break;
     }
     return check_launch("bilateral");
 }

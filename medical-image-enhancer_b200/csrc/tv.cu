@@ -25,9 +25,6 @@ namespace mdimg {
 namespace {
 
 constexpr int NT = 256;
-constexpr int TW = 64, TH = 32;
-constexpr int PW = TW + 2, PH = TH + 2, PP = PW + 1;   // p tiles with a 1-pixel halo
-constexpr int OW = TW + 1, OH = TH + 1, OP = OW + 1;   // out tile with +1 row / column
 
 struct TvState {             // per slice (position in sel)
     int stop_iter;           // index of the last executed loop body, -1 while running
@@ -48,22 +45,19 @@ __device__ __forceinline__ bool tv_stops(const double* E, int j, float w, float 
     return fabsf(__fsub_rn(ep, ej)) < __fmul_rn(eps, e0);
 }
 
-__device__ __forceinline__ float div_at(const float (*P0)[PP], const float (*P1)[PP], int r, int c,
-                                        int gy, int gx) {
-    // r, c index the halo tiles (tile origin at [1][1]); gy, gx are image coordinates
-    float dv = -__fadd_rn(P0[r][c], P1[r][c]);
-    if (gy > 0) dv = __fadd_rn(dv, P0[r - 1][c]);
-    if (gx > 0) dv = __fadd_rn(dv, P1[r][c - 1]);
-    return dv;
-}
+// One warp owns a strip of TV_COLS output columns x TV_ROWS rows and walks down the rows keeping
+// the previous / current / next row in registers.  x-neighbours come from warp shuffles: the warp
+// loads 32 consecutive columns starting one to the left of its strip, so lane 0 and lane 31 only
+// feed their neighbours (p1 of the column to the left, `out` of the column to the right).  No
+// shared memory, no block barrier, one pointer bump per row.  Out-of-image loads read as 0, which
+// reproduces the reference's slicing (d[1:] += p0[:-1] etc.) because x + 0.0f == x.
+constexpr int TV_COLS = 30;
+constexpr int TV_ROWS = 64;
 
 __global__ void __launch_bounds__(NT)
 k_tv_iter(const float* __restrict__ img, Dims d, int iter, const float* __restrict__ pin,
           float* __restrict__ pout, long long p_stride, double* __restrict__ energy, int max_iter,
           TvState* __restrict__ state, float w, float tau_over_w, float eps) {
-    __shared__ float P0[PH][PP], P1[PH][PP];
-    __shared__ float O[OH][OP];
-    __shared__ double red[2 * 32];
     const int si = blockIdx.y;
     if (state[si].stop_iter >= 0) return;
     const int s = slice_of(d.sel, si);
@@ -73,66 +67,83 @@ k_tv_iter(const float* __restrict__ img, Dims d, int iter, const float* __restri
         if (blockIdx.x == 0 && threadIdx.x == 0) state[si].stop_iter = iter - 1;
         return;
     }
-    const int tiles_x = (d.w + TW - 1) / TW;
-    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    const int x0 = tx * TW, y0 = ty * TH;
+    const int lane = threadIdx.x & 31;
+    const int strips_x = (d.w + TV_COLS - 1) / TV_COLS;
+    const int strips_y = (d.h + TV_ROWS - 1) / TV_ROWS;
+    const int wg = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    if (wg >= strips_x * strips_y) return;
+    const int sy = wg / strips_x, sx = wg - sy * strips_x;
+    const int c = sx * TV_COLS - 1 + lane;               // image column held by this lane
+    const int y0 = sy * TV_ROWS;
+    const int y1 = min(y0 + TV_ROWS, d.h);
+    const bool col_in = (c >= 0) && (c < d.w);
+    const bool owner = col_in && lane >= 1 && lane <= TV_COLS;   // lanes that store results
+    const bool has_right = c < d.w - 1;
     const size_t plane = (size_t)d.h * d.w;
-    const float* src = img + (size_t)s * plane;
-    const float* p0 = pin + (size_t)si * p_stride;
+    const int cc = col_in ? c : 0;
+    const float* src = img + (size_t)s * plane + cc;
+    const float* p0 = pin + (size_t)si * p_stride + cc;
     const float* p1 = p0 + plane;
-    float* q0 = pout + (size_t)si * p_stride;
+    float* q0 = pout + (size_t)si * p_stride + cc;
     float* q1 = q0 + plane;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    for (int i = tid; i < PH * PW; i += NT) {
-        int r = i / PW, c = i - r * PW;
-        int gy = y0 + r - 1, gx = x0 + c - 1;
-        float a = 0.0f, b = 0.0f;
-        if (gy >= 0 && gy < d.h && gx >= 0 && gx < d.w) {
-            a = p0[(size_t)gy * d.w + gx];
-            b = p1[(size_t)gy * d.w + gx];
+    // row y0 - 1 (only p0 is needed) and row y0
+    float up0 = (col_in && y0 > 0) ? p0[(size_t)(y0 - 1) * d.w] : 0.0f;
+    size_t off = (size_t)y0 * d.w;
+    float a0 = col_in ? p0[off] : 0.0f;
+    float a1 = col_in ? p1[off] : 0.0f;
+    float im = col_in ? src[off] : 0.0f;
+    float left = __shfl_up_sync(0xffffffffu, a1, 1);
+    float dcur = -__fadd_rn(a0, a1);
+    dcur = __fadd_rn(dcur, up0);
+    dcur = __fadd_rn(dcur, left);
+    float ocur = __fadd_rn(im, dcur);
+    float e_d2 = 0.0f, e_n = 0.0f;
+
+    // software pipeline: row y+1 is already in registers when row y is processed, and the loads
+    // of row y+2 are issued before any arithmetic of the iteration
+    bool nin = col_in && (y0 + 1 < d.h);
+    size_t noff = off + d.w;
+    float n0 = nin ? p0[noff] : 0.0f;
+    float n1 = nin ? p1[noff] : 0.0f;
+    float nim = nin ? src[noff] : 0.0f;
+#pragma unroll 2
+    for (int y = y0; y < y1; ++y) {
+        const size_t moff = noff + d.w;
+        const bool min_ = col_in && (y + 2 < d.h) && (y + 1 < y1);
+        const float m0 = min_ ? p0[moff] : 0.0f;
+        const float m1 = min_ ? p1[moff] : 0.0f;
+        const float mim = min_ ? src[moff] : 0.0f;
+
+        const float nleft = __shfl_up_sync(0xffffffffu, n1, 1);
+        float dn = -__fadd_rn(n0, n1);
+        dn = __fadd_rn(dn, a0);
+        dn = __fadd_rn(dn, nleft);
+        const float onext = __fadd_rn(nim, dn);
+        const float oright = __shfl_down_sync(0xffffffffu, ocur, 1);
+        const float g0 = (y < d.h - 1) ? __fsub_rn(onext, ocur) : 0.0f;
+        const float g1 = has_right ? __fsub_rn(oright, ocur) : 0.0f;
+        float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(g0, g0), __fmul_rn(g1, g1)));
+        if (owner) {
+            e_d2 += __fmul_rn(dcur, dcur);
+            e_n += nrm;
         }
-        P0[r][c] = a;
-        P1[r][c] = b;
+        nrm = __fadd_rn(__fmul_rn(nrm, tau_over_w), 1.0f);
+        const float r0 = __fdiv_rn(__fsub_rn(a0, __fmul_rn(0.25f, g0)), nrm);
+        const float r1 = __fdiv_rn(__fsub_rn(a1, __fmul_rn(0.25f, g1)), nrm);
+        if (owner) {
+            q0[off] = r0;
+            q1[off] = r1;
+        }
+        a0 = n0; a1 = n1; dcur = dn; ocur = onext; off = noff;
+        n0 = m0; n1 = m1; nim = mim; noff = moff;
     }
-    __syncthreads();
-    // out = x + d on the tile plus one extra row / column
-    double acc[2] = {0.0, 0.0};
-    for (int i = tid; i < OH * OW; i += NT) {
-        int r = i / OW, c = i - r * OW;
-        int gy = y0 + r, gx = x0 + c;
-        float o = 0.0f;
-        if (gy < d.h && gx < d.w) {
-            const float dv = div_at(P0, P1, r + 1, c + 1, gy, gx);
-            o = __fadd_rn(src[(size_t)gy * d.w + gx], dv);
-            if (r < TH && c < TW) acc[0] += (double)__fmul_rn(dv, dv);
-        }
-        O[r][c] = o;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j2 = 0; j2 < TH / 8; ++j2)
-#pragma unroll
-        for (int i2 = 0; i2 < TW / 32; ++i2) {
-            const int r = wid + 8 * j2, c = lane + 32 * i2;
-            const int gy = y0 + r, gx = x0 + c;
-            if (gy < d.h && gx < d.w) {
-                const float o = O[r][c];
-                const float g0 = gy < d.h - 1 ? __fsub_rn(O[r + 1][c], o) : 0.0f;
-                const float g1 = gx < d.w - 1 ? __fsub_rn(O[r][c + 1], o) : 0.0f;
-                float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(g0, g0), __fmul_rn(g1, g1)));
-                acc[1] += (double)nrm;
-                nrm = __fadd_rn(__fmul_rn(nrm, tau_over_w), 1.0f);
-                const float n0 = __fdiv_rn(__fsub_rn(P0[r + 1][c + 1], __fmul_rn(0.25f, g0)), nrm);
-                const float n1 = __fdiv_rn(__fsub_rn(P1[r + 1][c + 1], __fmul_rn(0.25f, g1)), nrm);
-                q0[(size_t)gy * d.w + gx] = n0;
-                q1[(size_t)gy * d.w + gx] = n1;
-            }
-        }
-    block_sum<2>(acc, red);
-    if (tid == 0) {
-        atomicAdd(&E[2 * iter], acc[0]);
-        atomicAdd(&E[2 * iter + 1], acc[1]);
+    // per-lane float32 partial sums (<= TV_ROWS terms) -> float64 across the warp
+    double sd = warp_sum((double)e_d2);
+    double sn = warp_sum((double)e_n);
+    if (lane == 0) {
+        atomicAdd(&E[2 * iter], sd);
+        atomicAdd(&E[2 * iter + 1], sn);
     }
 }
 
@@ -207,7 +218,8 @@ int tv_chambolle_run(const float* in, float* out, const Dims& d, double weight, 
     const float w = (float)weight;
     const float tau_over_w = (float)(0.25 / weight);
     const float epsf = (float)eps;
-    dim3 grid(((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH), d.n_sel);
+    const int n_warps = ((d.w + TV_COLS - 1) / TV_COLS) * ((d.h + TV_ROWS - 1) / TV_ROWS);
+    dim3 grid((n_warps + NT / 32 - 1) / (NT / 32), d.n_sel);
     int launched = 0;
     int* live_host = nullptr;
     cudaError_t herr = cudaMallocHost((void**)&live_host, sizeof(int));

@@ -110,6 +110,7 @@ class EnhanceResult:
     noise_guard: np.ndarray = field(default_factory=lambda: np.zeros(0, bool))
     over_processed: np.ndarray = field(default_factory=lambda: np.zeros(0, bool))
     tv_iterations: Optional[np.ndarray] = None
+    errors: Dict[int, str] = field(default_factory=dict)   # slice -> ValueError text (on_error='flag')
     sigma_before: Optional[torch.Tensor] = None     # device float64 [N], estimate_sigma(original)
     quality_before: Optional[torch.Tensor] = None   # device float64 [N, 2] (edge_ratio, niqe) of the original
 
@@ -142,9 +143,17 @@ class Engine:
 
     @staticmethod
     def _flush_checks(state: dict) -> None:
+        """Raise the reference's ValueError for the first failed check, or — in a stack call with
+        ``on_error='flag'`` — remember which slices failed and carry on with the others."""
         for flags, message in state.pop("checks", []):
-            if bool(flags.any().item()):
+            bad = flags.cpu().numpy() != 0
+            if not bad.any():
+                continue
+            if state.get("on_error", "raise") == "raise":
                 raise ValueError(message)
+            errs = state.setdefault("errors", {})
+            for i in np.flatnonzero(bad):
+                errs.setdefault(int(i), message)
 
     def _apply_step(self, name: str, q: ClampedParams, u_amount: float, cur: torch.Tensor,
                     tmp: torch.Tensor, sel: Optional[torch.Tensor], state: dict) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -236,14 +245,18 @@ class Engine:
 
     # ---- apply_enhancements_from_params -------------------------------------------------------
     def enhance_from_params(self, image: torch.Tensor, plan, *, sigma_before: Optional[torch.Tensor] = None,
-                            quality_before: Optional[torch.Tensor] = None) -> EnhanceResult:
+                            quality_before: Optional[torch.Tensor] = None,
+                            on_error: str = "raise") -> EnhanceResult:
+        """on_error='raise' mirrors the reference (ValueError when CLAHE sees a pixel outside [-1, 1]
+        or gamma a negative one); 'flag' is for stacks: the failing slices are returned unchanged
+        (a copy of the input) with their error text in ``EnhanceResult.errors``."""
         ops = self.ops
         n = image.shape[0]
         q = ClampedParams.from_params(plan.params)
         plan_ops = [op.lower().strip() for op in plan.recommended_ops]
         cur = image.clone()
         tmp = torch.empty_like(image)
-        state = {"nonneg": False, "tv_iters": None}
+        state = {"nonneg": False, "tv_iters": None, "on_error": on_error}
         common: List[str] = []
         for name in _STEP_ORDER:   # fixed order, gated by membership
             if name in plan_ops and self._enabled(name, q):
@@ -263,12 +276,13 @@ class Engine:
                 logger.warning(HALO_MSG)
                 reduced = q.u_amount * 0.5
                 ops.copy(image, cur, sel=sel)
-                st2 = {"nonneg": False, "tv_iters": None}
+                st2 = {"nonneg": False, "tv_iters": None, "on_error": on_error}
                 for op in plan_ops:
                     if op in _STEP_ORDER and self._enabled(op, q):
                         cur, tmp = self._apply_step(op, q, reduced, cur, tmp, sel, st2)
                 ops.clip01(cur, cur, sel=sel)
                 self._flush_checks(st2)
+                state.setdefault("errors", {}).update(st2.get("errors", {}))
                 for i in np.flatnonzero(halo):
                     labels[i].append(f"[safeguard] Unsharp reduced to {reduced:.2f}")
                 if st2["tv_iters"] is not None and tv_iters is not None:
@@ -291,8 +305,15 @@ class Engine:
             for i in np.flatnonzero(over):
                 labels[i].append("Blend-back 40% original (over-processing guard)")
 
+        errors = state.get("errors", {})
+        if errors:
+            bad = np.zeros(n, bool)
+            bad[list(errors)] = True
+            ops.copy(image, cur, sel=self._sel_tensor(bad))
+            for i, msg in errors.items():
+                labels[i] = [f"ERROR: {msg}"]
         return EnhanceResult(
-            image=cur, labels=labels, halo=halo, noise_guard=noise, over_processed=over,
+            image=cur, labels=labels, halo=halo, noise_guard=noise, over_processed=over, errors=errors,
             tv_iterations=None if tv_iters is None else tv_iters.cpu().numpy(),
             sigma_before=sigma_before, quality_before=quality_before,
         )

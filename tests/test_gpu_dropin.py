@@ -214,8 +214,11 @@ def test_stack_pipeline_matches_per_slice_calls(ops, synth):
     plan = synth.plan_full()
     res = process_stack(torch.from_numpy(raw.view(np.int16)).to(ops.device), plan, chunk=4)
     out_h, res_h = process_stack_host(raw, plan, chunk=4, ops=ops)
+    # float64 accumulators are combined with atomics (order not fixed), so the two runs agree to
+    # rounding of the sums, not to the bit
+    np.testing.assert_allclose(res.packed, res_h.packed, rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(res.tv_iterations, res_h.tv_iterations)
     np.testing.assert_array_equal(res.enhanced.cpu().numpy(), out_h)
-    np.testing.assert_array_equal(res.packed, res_h.packed)
     for z in (0, 5):
         x = omet.normalize_image(raw[z])
         ref, ref_labels = oenh.apply_enhancements_from_params(x, plan)

@@ -204,8 +204,10 @@ def test_bilateral(ops, dev, images, name, d):
     x = dev(im)
     out = torch.empty_like(x)
     ops.bilateral(x, out, d, 0.05, 0.05)
-    # d*d float32 exponentials per pixel: numpy's SIMD exp and CUDA expf differ by <= 2 ulp each
-    assert np.abs(host(out) - oenh.bilateral_filter(im, d, 0.05, 0.05)).max() <= 8 * ULP
+    # d*d float32 exponentials per pixel (numpy's SIMD exp is not correctly rounded, so the weights
+    # cannot match to the bit); float32 FMA accumulation here.  Stated tolerance: 16 float32 ulps
+    # (1.9e-6), an eighth of one 16-bit LSB.
+    assert np.abs(host(out) - oenh.bilateral_filter(im, d, 0.05, 0.05)).max() <= 16 * ULP
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -84,10 +84,8 @@ def process_chunk(ops: StackOps, raw: torch.Tensor, plan, keep_enhanced: bool = 
     n = raw.shape[0]
     x = ops.normalize(raw)
     rows_b = ops.metrics(x, with_niqe=True)
-    res = eng.enhance_from_params(
-        x, plan, sigma_before=rows_b[:, 0].contiguous(),
-        quality_before=rows_b[:, MC_EDGE_RATIO:MC_NIQE + 1].contiguous(), on_error="flag")
-    rows_a = ops.metrics(res.image, with_niqe=True)
+    res = eng.enhance_from_params(x, plan, rows_before=rows_b, on_error="flag")
+    rows_a = res.rows_after
     fr = ops.fullref(x, res.image)
     packed = torch.empty((n, PACK_COLS), dtype=torch.float64, device=ops.device)
     packed[:, :ROW_COLS] = rows_b

@@ -1,0 +1,91 @@
+// scipy.ndimage.uniform_filter on float32 tiles, the way scipy evaluates it: axis 0 then axis 1,
+// each pass a running window sum in double, scaled by 1/size and ROUNDED TO FLOAT32 before the
+// next pass.  Both passes slide a running sum (2 adds per output instead
+// of `size`), operands are kept in shared memory as doubles that already hold float32-rounded
+// values, so no conversion sits in the inner loops.
+//
+// Block = 256 threads (8 warps), output tile TH = 32 rows x TW = 64 columns.
+//   vertical   : thread = (column, row segment)           -> V[r][c]
+//   horizontal : lane = row, warp = 8-column segment      -> consume(r, c, mean...)
+// With an odd pitch (in doubles) both walks are shared-memory bank-conflict free.
+#pragma once
+#include "common.cuh"
+
+namespace mdimg {
+
+template <int K>
+struct BoxTile {
+    static constexpr int TW = 64, TH = 32;
+    static constexpr int XW = TW + K - 1;        // input columns (halo included)
+    static constexpr int XH = TH + K - 1;        // input rows
+    static constexpr int XP = XW | 1;            // odd pitch (doubles)
+    static constexpr int NSEG = 256 / XW;        // row segments per column in the vertical pass
+    static constexpr int RS = (TH + NSEG - 1) / NSEG;
+};
+
+// Single-step half-sample symmetric reflection (valid while the halo is smaller than n);
+// falls back to the general form for tiny images.
+__device__ __forceinline__ int refl_sym_fast(int i, int n) {
+    if (i < 0) i = -1 - i;
+    else if (i >= n) i = 2 * n - 1 - i;
+    if (i < 0 || i >= n) i = refl_sym(i, n);
+    return i;
+}
+
+__device__ __forceinline__ double round32(double v) { return (double)(float)v; }
+
+// Vertical pass for NQ quantities.  X[q]: [XH][XP] doubles, V[q]: [TH][XP] doubles.
+template <int K, int NQ>
+__device__ __forceinline__ void box_vertical(double* const (&X)[NQ], double* const (&V)[NQ], double inv) {
+    typedef BoxTile<K> T;
+    const int item = threadIdx.x;
+    if (item < T::XW * T::NSEG) {
+        const int sg = item / T::XW, c = item - sg * T::XW;
+        const int r0 = sg * T::RS;
+        const int r1 = min(r0 + T::RS, T::TH);
+        double s[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            s[q] = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) s[q] += X[q][(r0 + k) * T::XP + c];
+        }
+        for (int r = r0; r < r1; ++r) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                V[q][r * T::XP + c] = round32(s[q] * inv);
+                if (r + 1 < r1) s[q] += X[q][(r + K) * T::XP + c] - X[q][r * T::XP + c];
+            }
+        }
+    }
+}
+
+// Horizontal pass: calls f(r, c, m[NQ]) for the 8 pixels (r = lane, c = 8*warp .. 8*warp+7) with
+// m[q] = float32 box mean of quantity q.
+template <int K, int NQ, typename F>
+__device__ __forceinline__ void box_horizontal(double* const (&V)[NQ], double inv, F&& f) {
+    typedef BoxTile<K> T;
+    const int r = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int c0 = seg * 8;
+    double s[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) s[q] += V[q][r * T::XP + c0 + k];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float m[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) m[q] = (float)(s[q] * inv);
+        f(r, c0 + j, m);
+        if (j < 7) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                s[q] += V[q][r * T::XP + c0 + j + K] - V[q][r * T::XP + c0 + j];
+        }
+    }
+}
+
+}  // namespace mdimg

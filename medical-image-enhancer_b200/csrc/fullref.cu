@@ -6,6 +6,7 @@
 // double, scaled, rounded to float32 before the next pass; window [i-3, i+3] for size 7 and
 // [i-8, i+7] for size 16; half-sample symmetric border.
 #include "metrics.cuh"
+#include "boxfilter.cuh"
 
 namespace mdimg {
 
@@ -15,15 +16,14 @@ constexpr int NT = 256;
 constexpr int TW = 64, TH = 32;
 
 // ---------------- NIQE box-16 ----------------
-constexpr int B16L = 8, B16R = 7;
-constexpr int B16W = TW + B16L + B16R;   // 79
-constexpr int B16H = TH + B16L + B16R;   // 47
-constexpr int B16P = B16W + 1;
+typedef BoxTile<16> B16;
+constexpr int B16L = 8;   // window [i-8, i+7]
 
 struct Box16Smem {
-    float X[B16H][B16P];
-    float VS[TH][B16P];
-    float VQ[TH][B16P];
+    double X[B16::XH * B16::XP];
+    double Q[B16::XH * B16::XP];
+    double VS[B16::TH * B16::XP];
+    double VQ[B16::TH * B16::XP];
     double red[2 * 32];
 };
 
@@ -31,48 +31,41 @@ __global__ void __launch_bounds__(NT)
 k_box16_stats(const float* __restrict__ img, Dims d, double* __restrict__ acc2) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Box16Smem& sm = *reinterpret_cast<Box16Smem*>(smem_raw);
+    constexpr int XW = B16::XW, XH = B16::XH, XP = B16::XP;
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
     const int tiles_x = (d.w + TW - 1) / TW;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     const int x0 = tx * TW, y0 = ty * TH;
     const float* src = img + (size_t)s * d.h * d.w;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < B16H * B16W; i += NT) {
-        int r = i / B16W, c = i - r * B16W;
-        int gy = refl_sym(y0 + r - B16L, d.h), gx = refl_sym(x0 + c - B16L, d.w);
-        sm.X[r][c] = src[(size_t)gy * d.w + gx];
+    const int tid = threadIdx.x;
+    const bool interior = x0 >= B16L && y0 >= B16L && x0 + TW + 7 <= d.w && y0 + TH + 7 <= d.h;
+    for (int i = tid; i < XH * XW; i += NT) {
+        const int r = i / XW, c = i - r * XW;
+        int gy = y0 + r - B16L, gx = x0 + c - B16L;
+        if (!interior) { gy = refl_sym_fast(gy, d.h); gx = refl_sym_fast(gx, d.w); }
+        const float v = src[(size_t)gy * d.w + gx];
+        sm.X[r * XP + c] = (double)v;
+        sm.Q[r * XP + c] = (double)__fmul_rn(v, v);
     }
     __syncthreads();
-    for (int i = tid; i < TH * B16W; i += NT) {
-        int r = i / B16W, c = i - r * B16W;
-        double a = 0.0, q = 0.0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            float v = sm.X[r + k][c];
-            a += (double)v;
-            q += (double)__fmul_rn(v, v);
-        }
-        sm.VS[r][c] = (float)(a * 0.0625);
-        sm.VQ[r][c] = (float)(q * 0.0625);
+    {
+        double* const xin[2] = {sm.X, sm.Q};
+        double* const vout[2] = {sm.VS, sm.VQ};
+        box_vertical<16, 2>(xin, vout, 0.0625);
     }
     __syncthreads();
     double v[2] = {0.0, 0.0};
-#pragma unroll
-    for (int j = 0; j < TH / 8; ++j)
-#pragma unroll
-        for (int i = 0; i < TW / 32; ++i) {
-            const int r = wid + 8 * j, c = lane + 32 * i;
+    {
+        double* const vin[2] = {sm.VS, sm.VQ};
+        box_horizontal<16, 2>(vin, 0.0625, [&](int r, int c, const float (&m)[2]) {
             if (y0 + r < d.h && x0 + c < d.w) {
-                double ms = 0.0, mq = 0.0;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) { ms += (double)sm.VS[r][c + k]; mq += (double)sm.VQ[r][c + k]; }
-                const float m = (float)(ms * 0.0625), q = (float)(mq * 0.0625);
-                const float lv = fmaxf(__fsub_rn(q, __fmul_rn(m, m)), 0.0f);
-                v[0] += (double)lv;
-                v[1] += (double)lv * (double)lv;
+                const double lv = (double)fmaxf(__fsub_rn(m[1], __fmul_rn(m[0], m[0])), 0.0f);
+                v[0] += lv;
+                v[1] += lv * lv;
             }
-        }
+        });
+    }
     block_sum<2>(v, sm.red);
     if (tid == 0) {
         atomicAdd(&acc2[(size_t)si * 2 + 0], v[0]);
@@ -81,13 +74,13 @@ k_box16_stats(const float* __restrict__ img, Dims d, double* __restrict__ acc2) 
 }
 
 // ---------------- SSIM + PSNR ----------------
+typedef BoxTile<7> B7;
 constexpr int HALO = 3;
-constexpr int XW = TW + 2 * HALO, XH = TH + 2 * HALO, XP = XW + 1;
 
 struct SsimSmem {
-    float A[XH][XP];
-    float B[XH][XP];
-    float V[5][TH][XP];   // axis-0 means of a, b, a*a, b*b, a*b
+    float A[B7::XH * B7::XP];
+    float B[B7::XH * B7::XP];
+    double V[5][B7::TH * B7::XP];   // axis-0 means of a, b, a*a, b*b, a*b
     double red[2 * 32];
 };
 
@@ -96,6 +89,7 @@ k_ssim_psnr(const float* __restrict__ ia, const float* __restrict__ ib, Dims d,
             double* __restrict__ acc2) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SsimSmem& sm = *reinterpret_cast<SsimSmem*>(smem_raw);
+    constexpr int XW = B7::XW, XH = B7::XH, XP = B7::XP;
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
     const int tiles_x = (d.w + TW - 1) / TW;
@@ -103,54 +97,54 @@ k_ssim_psnr(const float* __restrict__ ia, const float* __restrict__ ib, Dims d,
     const int x0 = tx * TW, y0 = ty * TH;
     const float* pa = ia + (size_t)s * d.h * d.w;
     const float* pb = ib + (size_t)s * d.h * d.w;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
+    const bool interior = x0 >= HALO && y0 >= HALO && x0 + TW + HALO <= d.w && y0 + TH + HALO <= d.h;
     for (int i = tid; i < XH * XW; i += NT) {
-        int r = i / XW, c = i - r * XW;
-        int gy = refl_sym(y0 + r - HALO, d.h), gx = refl_sym(x0 + c - HALO, d.w);
-        size_t o = (size_t)gy * d.w + gx;
-        sm.A[r][c] = pa[o];
-        sm.B[r][c] = pb[o];
+        const int r = i / XW, c = i - r * XW;
+        int gy = y0 + r - HALO, gx = x0 + c - HALO;
+        if (!interior) { gy = refl_sym_fast(gy, d.h); gx = refl_sym_fast(gx, d.w); }
+        const size_t o = (size_t)gy * d.w + gx;
+        sm.A[r * XP + c] = pa[o];
+        sm.B[r * XP + c] = pb[o];
     }
     __syncthreads();
     const double inv7 = 1.0 / 7.0;
-    for (int i = tid; i < TH * XW; i += NT) {
-        int r = i / XW, c = i - r * XW;
-        double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
+    // axis-0 pass: sliding window; the five operands are formed (and rounded to float32, as
+    // numpy's im1 * im2 is) when a row enters or leaves the window
+    if (tid < XW * B7::NSEG) {
+        const int sg = tid / XW, c = tid - sg * XW;
+        const int r0 = sg * B7::RS, r1 = min(r0 + B7::RS, TH);
+        double sum[5] = {0, 0, 0, 0, 0};
+        auto add = [&](int r, double sign) {
+            const float a = sm.A[r * XP + c], b = sm.B[r * XP + c];
+            sum[0] += sign * (double)a;
+            sum[1] += sign * (double)b;
+            sum[2] += sign * (double)__fmul_rn(a, a);
+            sum[3] += sign * (double)__fmul_rn(b, b);
+            sum[4] += sign * (double)__fmul_rn(a, b);
+        };
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            float a = sm.A[r + k][c], b = sm.B[r + k][c];
-            sa += (double)a; sb += (double)b;
-            saa += (double)__fmul_rn(a, a); sbb += (double)__fmul_rn(b, b); sab += (double)__fmul_rn(a, b);
+        for (int k = 0; k < 7; ++k) add(r0 + k, 1.0);
+        for (int r = r0; r < r1; ++r) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) sm.V[q][r * XP + c] = round32(sum[q] * inv7);
+            if (r + 1 < r1) { add(r + 7, 1.0); add(r, -1.0); }
         }
-        sm.V[0][r][c] = (float)(sa * inv7); sm.V[1][r][c] = (float)(sb * inv7);
-        sm.V[2][r][c] = (float)(saa * inv7); sm.V[3][r][c] = (float)(sbb * inv7);
-        sm.V[4][r][c] = (float)(sab * inv7);
     }
     __syncthreads();
     const float cn = (float)(49.0 / 48.0);
     const float C1 = (float)1.0e-4, C2 = (float)9.0e-4;
     double v[2] = {0.0, 0.0};   // sum S over the crop, sum (a-b)^2 over the image
-#pragma unroll
-    for (int j = 0; j < TH / 8; ++j)
-#pragma unroll
-        for (int i = 0; i < TW / 32; ++i) {
-            const int r = wid + 8 * j, c = lane + 32 * i;
+    {
+        double* const vin[5] = {sm.V[0], sm.V[1], sm.V[2], sm.V[3], sm.V[4]};
+        box_horizontal<7, 5>(vin, inv7, [&](int r, int c, const float (&m)[5]) {
             const int gy = y0 + r, gx = x0 + c;
             if (gy < d.h && gx < d.w) {
-                const float a = sm.A[r + HALO][c + HALO], b = sm.B[r + HALO][c + HALO];
+                const float a = sm.A[(r + HALO) * XP + c + HALO], b = sm.B[(r + HALO) * XP + c + HALO];
                 const float df = __fsub_rn(a, b);
                 v[1] += (double)__fmul_rn(df, df);
                 if (gy >= HALO && gy < d.h - HALO && gx >= HALO && gx < d.w - HALO) {
-                    double m[5];
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        double t = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 7; ++k) t += (double)sm.V[q][r][c + k];
-                        m[q] = t * inv7;
-                    }
-                    const float ux = (float)m[0], uy = (float)m[1], uxx = (float)m[2],
-                                uyy = (float)m[3], uxy = (float)m[4];
+                    const float ux = m[0], uy = m[1], uxx = m[2], uyy = m[3], uxy = m[4];
                     const float vx = __fmul_rn(cn, __fsub_rn(uxx, __fmul_rn(ux, ux)));
                     const float vy = __fmul_rn(cn, __fsub_rn(uyy, __fmul_rn(uy, uy)));
                     const float vxy = __fmul_rn(cn, __fsub_rn(uxy, __fmul_rn(ux, uy)));
@@ -162,7 +156,8 @@ k_ssim_psnr(const float* __restrict__ ia, const float* __restrict__ ib, Dims d,
                     v[0] += (double)S;
                 }
             }
-        }
+        });
+    }
     block_sum<2>(v, sm.red);
     if (tid == 0) {
         atomicAdd(&acc2[(size_t)si * 2 + 0], v[0]);

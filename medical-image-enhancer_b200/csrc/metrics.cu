@@ -10,15 +10,13 @@
 //   k_grad_prep/k_grad_pass : the three |grad| statistics that depend on max / P90 of |grad|
 //   k_finalize      : the 16 numbers (+ mean, edge ratio, NIQE) per slice
 #include "metrics.cuh"
+#include "boxfilter.cuh"
 
 namespace mdimg {
 
 namespace {
 
 constexpr int TW = 64, TH = 32, HALO = 3;
-constexpr int XW = TW + 2 * HALO;   // 70
-constexpr int XH = TH + 2 * HALO;   // 38
-constexpr int XP = XW + 1;          // smem pitch
 constexpr int NT = 256;
 
 struct MetAcc {               // per slice, zero-initialised
@@ -50,22 +48,51 @@ __device__ __forceinline__ float lerp_np(float a, float b, float t) {
 
 // ---------------------------------------------------------------------------------------
 // Fused stencil statistics (one read of the image).
+//
+// Phases per 64x32 tile (256 threads):
+//   A  load tile + 3-pixel halo (half-sample symmetric border) into shared memory as doubles
+//      (x and the float32-rounded x*x): every later phase works on exact doubles, conversions
+//      happen once per loaded pixel;
+//   B  7-tap box mean along axis 0 (sliding window, boxfilter.cuh);
+//   C  7-tap box mean along axis 1 -> local std -> sum / sum of squares (nothing is stored);
+//   D  Laplacian + Sobel pair from a 3x3 register window sliding down 4 rows per thread,
+//      |grad| written to HBM (coalesced), clip counters, 256-bin histogram and the level-1 radix
+//      histograms of x and |grad| (warp-uniform fast path for flat regions such as CT air).
 // ---------------------------------------------------------------------------------------
+typedef BoxTile<7> B7;
+
 struct StencilSmem {
-    float X[XH][XP];
-    float VS[TH][XP];
-    float VQ[TH][XP];
+    double X[B7::XH * B7::XP];
+    double Q[B7::XH * B7::XP];
+    double VS[B7::TH * B7::XP];
+    double VQ[B7::TH * B7::XP];
     unsigned h256[256];
     unsigned hx[SEL_L1_BINS];
     unsigned hg[SEL_L1_BINS];
     double red[9 * 32];
 };
 
+// Shared-memory histogram increment; all 32 lanes must call.  Flat regions (every valid lane in
+// the same bin) cost one atomic per warp instead of a 32-way same-address serialisation.
+__device__ __forceinline__ void hist_add(unsigned* h, int bin, bool valid, int lane) {
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+    if (mask == 0) return;
+    const int leader = __ffs(mask) - 1;
+    const int b0 = __shfl_sync(0xffffffffu, bin, leader);
+    const bool same = !valid || bin == b0;
+    if (__all_sync(0xffffffffu, same)) {
+        if (lane == leader) atomicAdd(&h[b0], (unsigned)__popc(mask));
+    } else if (valid) {
+        atomicAdd(&h[bin], 1u);
+    }
+}
+
 __global__ void __launch_bounds__(NT)
 k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
                 float* __restrict__ gout, unsigned* __restrict__ l1x, unsigned* __restrict__ l1g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StencilSmem& sm = *reinterpret_cast<StencilSmem*>(smem_raw);
+    constexpr int XW = B7::XW, XH = B7::XH, XP = B7::XP;
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
     const int tiles_x = (d.w + TW - 1) / TW;
@@ -77,89 +104,101 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
     for (int i = tid; i < 256; i += NT) sm.h256[i] = 0;
     for (int i = tid; i < SEL_L1_BINS; i += NT) { sm.hx[i] = 0; sm.hg[i] = 0; }
 
-    // tile + halo, half-sample symmetric border (scipy.ndimage mode='reflect')
+    // ---- A: tile + halo ----
+    const bool interior = x0 >= HALO && y0 >= HALO && x0 + TW + HALO <= d.w && y0 + TH + HALO <= d.h;
     for (int i = tid; i < XH * XW; i += NT) {
-        int r = i / XW, c = i - r * XW;
-        int gy = refl_sym(y0 + r - HALO, d.h);
-        int gx = refl_sym(x0 + c - HALO, d.w);
-        sm.X[r][c] = src[(size_t)gy * d.w + gx];
+        const int r = i / XW, c = i - r * XW;
+        int gy = y0 + r - HALO, gx = x0 + c - HALO;
+        if (!interior) { gy = refl_sym_fast(gy, d.h); gx = refl_sym_fast(gx, d.w); }
+        const float v = src[(size_t)gy * d.w + gx];
+        sm.X[r * XP + c] = (double)v;
+        sm.Q[r * XP + c] = (double)__fmul_rn(v, v);
     }
     __syncthreads();
 
-    // axis-0 pass of uniform_filter(size=7) on x and x*x: double sum, /7, round to float32
+    // ---- B: axis-0 box means ----
     const double inv7 = 1.0 / 7.0;
-    for (int i = tid; i < TH * XW; i += NT) {
-        int r = i / XW, c = i - r * XW;
-        double a = 0.0, q = 0.0;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            float v = sm.X[r + k][c];
-            a += (double)v;
-            q += (double)__fmul_rn(v, v);
-        }
-        sm.VS[r][c] = (float)(a * inv7);
-        sm.VQ[r][c] = (float)(q * inv7);
+    {
+        double* const xin[2] = {sm.X, sm.Q};
+        double* const vout[2] = {sm.VS, sm.VQ};
+        box_vertical<7, 2>(xin, vout, inv7);
     }
     __syncthreads();
 
     double acc_v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+    // ---- C: axis-1 box means -> local std ----
+    {
+        double* const vin[2] = {sm.VS, sm.VQ};
+        double ls1 = 0.0, ls2 = 0.0;
+        box_horizontal<7, 2>(vin, inv7, [&](int r, int c, const float (&m)[2]) {
+            if (y0 + r < d.h && x0 + c < d.w) {
+                const float lv = fmaxf(__fsub_rn(m[1], __fmul_rn(m[0], m[0])), 0.0f);
+                const double ls = (double)__fsqrt_rn(lv);
+                ls1 += ls;
+                ls2 += ls * ls;
+            }
+        });
+        acc_v[7] = ls1;
+        acc_v[8] = ls2;
+    }
+
+    // ---- D: 3x3 stencils ----
     unsigned c_low = 0, c_high = 0, c_lt0 = 0, c_gt1 = 0;
     float gmax = 0.0f;
+    float f_lap = 0.0f, f_lap2 = 0.0f, f_abs = 0.0f, f_g = 0.0f, f_g2 = 0.0f;
+    double d_x = 0.0, d_x2 = 0.0;
     float* gdst = gout + (size_t)s * d.h * d.w;
-
 #pragma unroll
-    for (int j = 0; j < TH / 8; ++j) {
+    for (int i = 0; i < TW / 32; ++i) {
+        const int c = lane + 32 * i;
+        const int cc = c + HALO;
+        const int gx = x0 + c;
+        const int rbase = wid * 4;
+        const double* col = sm.X + (rbase + HALO - 1) * XP + cc;
+        double u0 = col[-1], u1 = col[0], u2 = col[1];
+        double m0 = col[XP - 1], m1 = col[XP], m2 = col[XP + 1];
 #pragma unroll
-        for (int i = 0; i < TW / 32; ++i) {
-            const int r = wid + 8 * j, c = lane + 32 * i;
-            const int gy = y0 + r, gx = x0 + c;
-            if (gy < d.h && gx < d.w) {
-                const int rr = r + HALO, cc = c + HALO;
-                const float xc = sm.X[rr][cc];
-                const double n00 = sm.X[rr - 1][cc - 1], n01 = sm.X[rr - 1][cc], n02 = sm.X[rr - 1][cc + 1];
-                const double n10 = sm.X[rr][cc - 1], n12 = sm.X[rr][cc + 1];
-                const double n20 = sm.X[rr + 1][cc - 1], n21 = sm.X[rr + 1][cc], n22 = sm.X[rr + 1][cc + 1];
-                // scipy.ndimage.convolve accumulates in double and stores float32
-                const float lap = (float)(4.0 * (double)xc - n01 - n10 - n12 - n21);
-                const float sh = (float)(0.25 * (n00 - n20) + 0.5 * (n01 - n21) + 0.25 * (n02 - n22));
-                const float sv = (float)(0.25 * (n00 - n02) + 0.5 * (n10 - n12) + 0.25 * (n20 - n22));
-                const float g = __fsqrt_rn(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
+        for (int j = 0; j < 4; ++j) {
+            const int r = rbase + j;
+            const int gy = y0 + r;
+            const double* dn = sm.X + (r + HALO + 1) * XP + cc;
+            const double n0 = dn[-1], n1 = dn[0], n2 = dn[1];
+            const bool valid = gy < d.h && gx < d.w;
+            // scipy.ndimage.convolve: exact double accumulation, one rounding to float32
+            const float lap = (float)(4.0 * m1 - u1 - m0 - m2 - n1);
+            const float sh = (float)(0.25 * (u0 - n0) + 0.5 * (u1 - n1) + 0.25 * (u2 - n2));
+            const float sv = (float)(0.25 * (u0 - u2) + 0.5 * (m0 - m2) + 0.25 * (n0 - n2));
+            const float g = __fsqrt_rn(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
+            const float xc = (float)m1;
+            int b256 = (int)(xc * 256.0f);
+            b256 = b256 > 255 ? 255 : b256;
+            if (valid) {
                 gdst[(size_t)gy * d.w + gx] = g;
                 gmax = fmaxf(gmax, g);
-
-                // axis-1 pass of the 7x7 box means
-                double ms = 0.0, mq = 0.0;
-#pragma unroll
-                for (int k = 0; k < 7; ++k) { ms += (double)sm.VS[r][c + k]; mq += (double)sm.VQ[r][c + k]; }
-                const float m = (float)(ms * inv7), q = (float)(mq * inv7);
-                const float lv = fmaxf(__fsub_rn(q, __fmul_rn(m, m)), 0.0f);
-                const float ls = __fsqrt_rn(lv);
-
-                acc_v[0] += (double)xc;
-                acc_v[1] += (double)xc * (double)xc;
-                acc_v[2] += (double)lap;
-                acc_v[3] += (double)__fmul_rn(lap, lap);
-                acc_v[4] += (double)fabsf(lap);
-                acc_v[5] += (double)g;
-                acc_v[6] += (double)g * (double)g;
-                acc_v[7] += (double)ls;
-                acc_v[8] += (double)ls * (double)ls;
+                d_x += m1;
+                d_x2 += m1 * m1;
+                f_lap += lap;
+                f_lap2 = fmaf(lap, lap, f_lap2);
+                f_abs += fabsf(lap);
+                f_g += g;
+                f_g2 = fmaf(g, g, f_g2);
                 c_low += (xc <= 0.01f);
                 c_high += (xc >= 0.99f);
                 c_lt0 += (xc < 0.0f);
                 c_gt1 += (xc > 1.0f);
-
-                // np.histogram(bins=256, range=(0,1)): exact power-of-two edges
-                if (xc >= 0.0f && xc <= 1.0f) {
-                    int b = (int)(xc * 256.0f);
-                    if (b > 255) b = 255;
-                    atomicAdd(&sm.h256[b], 1u);
-                }
-                atomicAdd(&sm.hx[f2key(xc) >> 21], 1u);
-                atomicAdd(&sm.hg[f2key(g) >> 21], 1u);
             }
+            // np.histogram(bins=256, range=(0,1)): exact power-of-two edges, out-of-range dropped
+            hist_add(sm.h256, b256, valid && xc >= 0.0f && xc <= 1.0f, lane);
+            hist_add(sm.hx, (int)(f2key(xc) >> 21), valid, lane);
+            hist_add(sm.hg, (int)(f2key(g) >> 21), valid, lane);
+            u0 = m0; u1 = m1; u2 = m2;
+            m0 = n0; m1 = n1; m2 = n2;
         }
     }
+    acc_v[0] = d_x; acc_v[1] = d_x2;
+    acc_v[2] = (double)f_lap; acc_v[3] = (double)f_lap2; acc_v[4] = (double)f_abs;
+    acc_v[5] = (double)f_g; acc_v[6] = (double)f_g2;
     __syncthreads();
 
     block_sum<9>(acc_v, sm.red);

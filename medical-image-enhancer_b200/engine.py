@@ -113,6 +113,7 @@ class EnhanceResult:
     errors: Dict[int, str] = field(default_factory=dict)   # slice -> ValueError text (on_error='flag')
     sigma_before: Optional[torch.Tensor] = None     # device float64 [N], estimate_sigma(original)
     quality_before: Optional[torch.Tensor] = None   # device float64 [N, 2] (edge_ratio, niqe) of the original
+    rows_after: Optional[torch.Tensor] = None       # device float64 [N, 24]: mdimg_metrics rows of `image`
 
 
 _STEP_ORDER = ("denoise", "clahe", "gamma", "unsharp", "post_denoise", "bilateral", "tv_denoise")
@@ -246,6 +247,7 @@ class Engine:
     # ---- apply_enhancements_from_params -------------------------------------------------------
     def enhance_from_params(self, image: torch.Tensor, plan, *, sigma_before: Optional[torch.Tensor] = None,
                             quality_before: Optional[torch.Tensor] = None,
+                            rows_before: Optional[torch.Tensor] = None,
                             on_error: str = "raise") -> EnhanceResult:
         """on_error='raise' mirrors the reference (ValueError when CLAHE sees a pixel outside [-1, 1]
         or gamma a negative one); 'flag' is for stacks: the failing slices are returned unchanged
@@ -267,10 +269,31 @@ class Engine:
         labels = [list(common) for _ in range(n)]
         tv_iters = state["tv_iters"]
 
+        # ---- safeguards -------------------------------------------------------------------------
+        # One fused metrics pass over the current stack yields everything the three guards look at
+        # (edge ratio, estimate_sigma, NIQE approximation) AND the compute_metrics rows of the final
+        # image; only slices a guard actually modifies are measured again.
+        if rows_before is not None:
+            s0h = rows_before[:, 0].cpu().numpy()
+            nb = rows_before[:, MC_NIQE].cpu().numpy()
+        else:
+            if sigma_before is None:
+                sigma_before = ops.estimate_sigma(image)
+            if quality_before is None:
+                quality_before = ops.quality(image, niqe=True)
+            s0h = sigma_before.cpu().numpy()
+            nb = quality_before[:, 1].cpu().numpy()
+        rows = ops.metrics(cur, with_niqe=True)
+
+        def remeasure(mask: np.ndarray) -> None:
+            sel_ = self._sel_tensor(mask)
+            if sel_ is not None:
+                ops.metrics(cur, with_niqe=True, sel=sel_, out=rows)
+
+        rows_h = rows.cpu().numpy()
         halo = np.zeros(n, bool)
         if "unsharp" in plan_ops:   # _check_halo -> re-run in the plan's own order with amount / 2
-            er = ops.quality(cur, niqe=False)[:, 0].cpu().numpy()
-            halo = er > 1.5
+            halo = rows_h[:, MC_EDGE_RATIO] > 1.5
             sel = self._sel_tensor(halo)
             if sel is not None:
                 logger.warning(HALO_MSG)
@@ -287,35 +310,45 @@ class Engine:
                     labels[i].append(f"[safeguard] Unsharp reduced to {reduced:.2f}")
                 if st2["tv_iters"] is not None and tv_iters is not None:
                     tv_iters = torch.where(torch.from_numpy(halo).to(ops.device), st2["tv_iters"], tv_iters)
+                remeasure(halo)
+                rows_h = rows.cpu().numpy()
 
-        noise, sigma_before = self._noise_guard(image, cur, labels, sigma_before)
+        # _check_noise_amplification -> corrective light denoise (enhancement.py:55-63,356-360)
+        with np.errstate(invalid="ignore"):
+            noise = (~(s0h < 1e-8)) & (rows_h[:, 0] > s0h * 1.3)
+        sel = self._sel_tensor(noise)
+        if sel is not None:
+            logger.warning(NOISE_MSG)
+            ops.light_denoise(cur, cur, 0.4, sel=sel)
+            ops.clip01(cur, cur, sel=sel)
+            for i in np.flatnonzero(noise):
+                labels[i].append("Auto-corrective denoise (noise guard)")
+            remeasure(noise)
+            rows_h = rows.cpu().numpy()
 
         # _check_over_processing: NIQE-approx degradation > 0.5 -> 0.6*enhanced + 0.4*original
-        if quality_before is None:
-            quality_before = ops.quality(image, niqe=True)
-        qa = ops.quality(cur, niqe=True)
-        nb = quality_before[:, 1].cpu().numpy()
-        na = qa[:, 1].cpu().numpy()
         with np.errstate(invalid="ignore"):
-            over = (na - nb) > 0.5
+            over = (rows_h[:, MC_NIQE] - nb) > 0.5
         sel = self._sel_tensor(over)
         if sel is not None:
             logger.warning(OVER_MSG)
             ops.axpby(cur, image, cur, 0.6, 0.4, clip01=True, sel=sel)
             for i in np.flatnonzero(over):
                 labels[i].append("Blend-back 40% original (over-processing guard)")
+            remeasure(over)
 
         errors = state.get("errors", {})
         if errors:
             bad = np.zeros(n, bool)
             bad[list(errors)] = True
             ops.copy(image, cur, sel=self._sel_tensor(bad))
+            remeasure(bad)
             for i, msg in errors.items():
                 labels[i] = [f"ERROR: {msg}"]
         return EnhanceResult(
             image=cur, labels=labels, halo=halo, noise_guard=noise, over_processed=over, errors=errors,
             tv_iterations=None if tv_iters is None else tv_iters.cpu().numpy(),
-            sigma_before=sigma_before, quality_before=quality_before,
+            sigma_before=sigma_before, quality_before=quality_before, rows_after=rows,
         )
 
     # ---- apply_enhancements (issue-gated defaults) ------------------------------------------------

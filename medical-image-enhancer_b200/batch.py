@@ -3,9 +3,9 @@
 This is the batch form of what the reference's runner does per image
 (``normalize_image`` -> ``apply_enhancements_from_params`` -> ``compute_metrics(enhanced)`` +
 ``compute_validation(original, enhanced)``; pipeline/runner.py:80-153, pipeline/tools.py:113-141).
-Slices are independent, so a stack is processed in chunks sized to keep one chunk's working set
-(input, current, scratch, TV state) inside the 126 MB L2: the multi-pass steps (TV iterations,
-radix-select refinements, CLAHE passes) then re-read L2, not HBM.
+Slices are independent, so a stack is processed in large chunks (default ~128 Mpx): every kernel
+launch then covers tens of thousands of CTAs and the per-launch / per-safeguard host round trips
+are amortised over hundreds of slices.
 
 Results identical to per-slice calls; ``compute_metrics`` of the same image is evaluated once
 per image (the reference recomputes the same values up to four times).
@@ -71,11 +71,13 @@ class StackResult:
         return np.array([self.score(i)[0] for i in range(self.packed.shape[0])])
 
 
-def default_chunk(h: int, w: int, l2_bytes: int = 126 << 20) -> int:
-    """Slices per chunk so that ~9 float32 images per slice (input, current, scratch, 4 planes of TV
-    state, |grad| buffer, pyramid) stay L2-resident; never below 4 slices."""
-    per_slice = 9 * 4 * h * w
-    return int(max(4, min(1024, (l2_bytes * 3 // 4) // max(per_slice, 1))))
+def default_chunk(h: int, w: int, px_budget: int = 1 << 27) -> int:
+    """Slices per chunk.  Measured on B200 (profiles/r01_chunk_sweep.txt): the kernels are
+    instruction- and latency-bound, not L2-capacity-bound, so large launches win — a chunk is
+    sized to ~128 Mpx (512 slices of 512x512, 14 radiographs of 3000x3000), which keeps every grid
+    in the tens of thousands of CTAs while leaving several chunks per stack for the host<->device
+    copy pipeline of the end-to-end path."""
+    return int(max(1, min(4096, px_budget // max(h * w, 1))))
 
 
 def process_chunk(ops: StackOps, raw: torch.Tensor, plan, keep_enhanced: bool = True):

@@ -230,7 +230,7 @@ def run_gpu(args) -> None:
         torch.cuda.synchronize()
 
     def step_resident():
-        res = process_stack(raw_dev, plan, chunk=chunk, keep_enhanced=True, ops=ops)
+        res = process_stack(raw_dev, plan, chunk=chunk, keep_enhanced=True, ops=ops, workers=args.workers)
         if world > 1:   # the only exchange: per-slice metric / validation rows
             rows = torch.from_numpy(res.packed).to(device)
             dist.all_gather_into_tensor(gathered, rows)
@@ -246,18 +246,27 @@ def run_gpu(args) -> None:
             dist.all_gather_into_tensor(gathered, rows)
         return res
 
+    per_step = []
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         barrier()
         l0 = ops.lib.mdimg_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         e0.record()
-        for _ in range(steps):
+        for i in range(steps):
             last = fn()
+            marks[i].record()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        prev = e0
+        per_step.clear()
+        for mk in marks:
+            per_step.append(round(prev.elapsed_time(mk), 2))
+            prev = mk
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -267,6 +276,7 @@ def run_gpu(args) -> None:
     if rank == 0:
         sampler.start()
     ms_total, launches, last = timed(step_resident, args.steps, args.warmup)
+    steps_ms = list(per_step)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _, _ = timed(step_e2e, max(1, min(args.steps, 2)), 1)
     e2e_steps = max(1, min(args.steps, 2))
@@ -318,9 +328,9 @@ def run_gpu(args) -> None:
             "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "slices_per_gpu": n, "chunk_slices": chunk,
+            "config": {"workload": WORKLOAD, "slices_per_gpu": n, "chunk_slices": chunk, "workers": args.workers,
                        "l2": "input stack (512 MiB u16 per GPU) is larger than L2; no flush needed",
-                       "images_per_s": value * 1e6 / (H * W)},
+                       "images_per_s": value * 1e6 / (H * W), "ms_each_step_rank0": steps_ms},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpx/s",
                     "h2d_bytes_per_step": int(n * H * W * 2),
@@ -342,7 +352,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slices", type=int, default=1024, help="slices per GPU")
-    ap.add_argument("--chunk", type=int, default=0, help="slices per L2-resident chunk (0 = auto)")
+    ap.add_argument("--chunk", type=int, default=0, help="slices per chunk (0 = auto)")
+    ap.add_argument("--workers", type=int, default=2, help="host threads / CUDA streams driving chunks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

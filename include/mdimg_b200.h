@@ -14,7 +14,7 @@
  *    indexed by slice keep their position in the full stack;
  *  - the caller owns all buffers; scratch memory is a caller-provided device workspace whose
  *    size is queried with mdimg_workspace_bytes(); nothing is allocated behind the caller's back
- *    except one pinned int per mdimg_tv_chambolle call;
+ *    except one pinned int per host thread that calls mdimg_tv_chambolle;
  *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream unless
  *    noted; results in device memory are valid after the stream is synchronised;
  *  - every function returns MDIMG_OK (0) or an error code; mdimg_last_error() returns a

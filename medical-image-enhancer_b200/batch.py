@@ -13,6 +13,7 @@ per image (the reference recomputes the same values up to four times).
 
 from __future__ import annotations
 
+import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -106,23 +107,70 @@ def process_chunk(ops: StackOps, raw: torch.Tensor, plan, keep_enhanced: bool = 
 
 
 def process_stack(raw: torch.Tensor, plan, chunk: Optional[int] = None, keep_enhanced: bool = True,
-                  ops: Optional[StackOps] = None) -> StackResult:
+                  ops: Optional[StackOps] = None, workers: int = 2) -> StackResult:
     """Device-resident stack (uint16 bit pattern in an int16/uint16 tensor, or float32) ->
-    enhanced stack + per-slice metric / validation rows."""
+    enhanced stack + per-slice metric / validation rows.
+
+    Chunks are independent, so `workers` host threads drive them on separate CUDA streams: the
+    small latency-bound kernels, launch gaps and safeguard round trips of one chunk overlap with
+    the other chunk's work (the scratch workspace is per thread)."""
     ops = ops or get_ops(raw.device)
     n, h, w = raw.shape
     chunk = chunk or default_chunk(h, w)
+    spans = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
+    workers = max(1, min(workers, len(spans)))
     enhanced = torch.empty((n, h, w), dtype=torch.float32, device=ops.device) if keep_enhanced else None
     packed_dev = torch.empty((n, PACK_COLS), dtype=torch.float64, device=ops.device)
-    labels: List[List[str]] = []
-    for a in range(0, n, chunk):
-        b = min(n, a + chunk)
+    labels: List[Optional[List[List[str]]]] = [None] * len(spans)
+
+    def run_span(i: int) -> None:
+        a, b = spans[i]
         enh, packed, lab = process_chunk(ops, raw[a:b], plan, keep_enhanced)
         if keep_enhanced:
             enhanced[a:b] = enh
         packed_dev[a:b] = packed
-        labels.extend(lab)
-    return StackResult(enhanced=enhanced, packed=packed_dev.cpu().numpy(), labels=labels)
+        labels[i] = lab
+
+    if workers == 1:
+        for i in range(len(spans)):
+            run_span(i)
+    else:
+        main = torch.cuda.current_stream(ops.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        streams = _worker_streams(ops.device, workers)
+        errors: List[BaseException] = []
+
+        def worker(k: int) -> None:
+            try:
+                with torch.cuda.device(ops.device), torch.cuda.stream(streams[k]):
+                    streams[k].wait_event(ready)
+                    for i in range(k, len(spans), workers):
+                        run_span(i)
+            except BaseException as exc:  # noqa: BLE001 - re-raised on the caller's thread
+                errors.append(exc)
+
+        threads = [threading.Thread(target=worker, args=(k,), daemon=True) for k in range(workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for st in streams:
+            main.wait_stream(st)
+        if errors:
+            raise errors[0]
+    flat = [lab for part in labels for lab in (part or [])]
+    return StackResult(enhanced=enhanced, packed=packed_dev.cpu().numpy(), labels=flat)
+
+
+_stream_cache: dict = {}
+
+
+def _worker_streams(device: torch.device, count: int):
+    key = (device.index, count)
+    if key not in _stream_cache:
+        _stream_cache[key] = [torch.cuda.Stream(device) for _ in range(count)]
+    return _stream_cache[key]
 
 
 def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,

@@ -16,6 +16,7 @@
 // therefore done in float32 FMAs (tap order kept) instead of emulating numpy's float64-add /
 // float32-store per tap.  Measured difference to the oracle: a few float32 ulps (tests allow 16).
 #include "enhance.cuh"
+#include "boxfilter.cuh"
 
 namespace mdimg {
 
@@ -41,11 +42,7 @@ k_bilateral(const float* __restrict__ in, float* __restrict__ out, Dims d, const
     const float* src = in + (size_t)s * d.h * d.w;
     float* dst = out + (size_t)s * d.h * d.w;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < XH * XW; i += NT) {
-        int r = i / XW, c = i - r * XW;
-        int gy = refl_mirror(y0 + r - R, d.h), gx = refl_mirror(x0 + c - R, d.w);
-        X[r][c] = src[(size_t)gy * d.w + gx];
-    }
+    load_tile<XW, XH, R, 1>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) { X[r][c] = v; });
     __syncthreads();
 #pragma unroll
     for (int j2 = 0; j2 < TH / 8; ++j2)

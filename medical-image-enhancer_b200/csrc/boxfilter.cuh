@@ -34,6 +34,33 @@ __device__ __forceinline__ int refl_sym_fast(int i, int n) {
 
 __device__ __forceinline__ double round32(double v) { return (double)(float)v; }
 
+// Cooperative tile load, one warp per tile row: the (<= 3) column indices of a lane are resolved
+// once, the row index once per row, so the inner loop is one add + one load + the caller's store.
+// REFLECT: 0 = half-sample symmetric (scipy 'reflect'), 1 = whole-sample mirror (np.pad 'reflect').
+template <int XW, int XH, int HL, int REFLECT, typename Store>
+__device__ __forceinline__ void load_tile(const float* __restrict__ src, int h, int w, int x0, int y0,
+                                          Store&& store) {
+    static_assert(XW <= 96, "at most three columns per lane");
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int gx[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int c = lane + 32 * k;
+        const int x = x0 + c - HL;
+        gx[k] = REFLECT == 0 ? refl_sym_fast(x, w) : refl_mirror(x, w);
+    }
+    for (int r = wid; r < XH; r += nw) {
+        const int y = y0 + r - HL;
+        const int gy = REFLECT == 0 ? refl_sym_fast(y, h) : refl_mirror(y, h);
+        const float* row = src + (size_t)gy * w;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int c = lane + 32 * k;
+            if (c < XW) store(r, c, row[gx[k]]);
+        }
+    }
+}
+
 // Vertical pass for NQ quantities.  X[q]: [XH][XP] doubles, V[q]: [TH][XP] doubles.
 template <int K, int NQ>
 __device__ __forceinline__ void box_vertical(double* const (&X)[NQ], double* const (&V)[NQ], double inv) {

@@ -39,15 +39,10 @@ k_box16_stats(const float* __restrict__ img, Dims d, double* __restrict__ acc2) 
     const int x0 = tx * TW, y0 = ty * TH;
     const float* src = img + (size_t)s * d.h * d.w;
     const int tid = threadIdx.x;
-    const bool interior = x0 >= B16L && y0 >= B16L && x0 + TW + 7 <= d.w && y0 + TH + 7 <= d.h;
-    for (int i = tid; i < XH * XW; i += NT) {
-        const int r = i / XW, c = i - r * XW;
-        int gy = y0 + r - B16L, gx = x0 + c - B16L;
-        if (!interior) { gy = refl_sym_fast(gy, d.h); gx = refl_sym_fast(gx, d.w); }
-        const float v = src[(size_t)gy * d.w + gx];
+    load_tile<XW, XH, B16L, 0>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) {
         sm.X[r * XP + c] = (double)v;
         sm.Q[r * XP + c] = (double)__fmul_rn(v, v);
-    }
+    });
     __syncthreads();
     {
         double* const xin[2] = {sm.X, sm.Q};
@@ -98,15 +93,8 @@ k_ssim_psnr(const float* __restrict__ ia, const float* __restrict__ ib, Dims d,
     const float* pa = ia + (size_t)s * d.h * d.w;
     const float* pb = ib + (size_t)s * d.h * d.w;
     const int tid = threadIdx.x;
-    const bool interior = x0 >= HALO && y0 >= HALO && x0 + TW + HALO <= d.w && y0 + TH + HALO <= d.h;
-    for (int i = tid; i < XH * XW; i += NT) {
-        const int r = i / XW, c = i - r * XW;
-        int gy = y0 + r - HALO, gx = x0 + c - HALO;
-        if (!interior) { gy = refl_sym_fast(gy, d.h); gx = refl_sym_fast(gx, d.w); }
-        const size_t o = (size_t)gy * d.w + gx;
-        sm.A[r * XP + c] = pa[o];
-        sm.B[r * XP + c] = pb[o];
-    }
+    load_tile<XW, XH, HALO, 0>(pa, d.h, d.w, x0, y0, [&](int r, int c, float v) { sm.A[r * XP + c] = v; });
+    load_tile<XW, XH, HALO, 0>(pb, d.h, d.w, x0, y0, [&](int r, int c, float v) { sm.B[r * XP + c] = v; });
     __syncthreads();
     const double inv7 = 1.0 / 7.0;
     // axis-0 pass: sliding window; the five operands are formed (and rounded to float32, as

@@ -105,15 +105,10 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
     for (int i = tid; i < SEL_L1_BINS; i += NT) { sm.hx[i] = 0; sm.hg[i] = 0; }
 
     // ---- A: tile + halo ----
-    const bool interior = x0 >= HALO && y0 >= HALO && x0 + TW + HALO <= d.w && y0 + TH + HALO <= d.h;
-    for (int i = tid; i < XH * XW; i += NT) {
-        const int r = i / XW, c = i - r * XW;
-        int gy = y0 + r - HALO, gx = x0 + c - HALO;
-        if (!interior) { gy = refl_sym_fast(gy, d.h); gx = refl_sym_fast(gx, d.w); }
-        const float v = src[(size_t)gy * d.w + gx];
+    load_tile<XW, XH, HALO, 0>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) {
         sm.X[r * XP + c] = (double)v;
         sm.Q[r * XP + c] = (double)__fmul_rn(v, v);
-    }
+    });
     __syncthreads();
 
     // ---- B: axis-0 box means ----

@@ -7,6 +7,7 @@
 // and rounded to float32 when stored.  Both passes run from one shared-memory tile, so the slice
 // is read once and written once.
 #include "enhance.cuh"
+#include "boxfilter.cuh"
 
 namespace mdimg {
 
@@ -34,11 +35,7 @@ k_unsharp(const float* __restrict__ in, float* __restrict__ out, Dims d, float a
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float lo = (mm && key2f(mm[s].x) < 0.0f) ? -1.0f : 0.0f;   // vrange when any pixel is negative
 
-    for (int i = tid; i < XH * XW; i += NT) {
-        int r = i / XW, c = i - r * XW;
-        int gy = refl_sym(y0 + r - R, d.h), gx = refl_sym(x0 + c - R, d.w);
-        X[r][c] = src[(size_t)gy * d.w + gx];
-    }
+    load_tile<XW, XH, R, 0>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) { X[r][c] = v; });
     __syncthreads();
     for (int i = tid; i < TH * XW; i += NT) {
         int r = i / XW, c = i - r * XW;

@@ -16,6 +16,12 @@
 #include "enhance.cuh"
 #include "select.cuh"
 
+#include <map>
+#include <memory>
+#include <mutex>
+#include <utility>
+#include <vector>
+
 namespace mdimg {
 
 namespace {
@@ -55,7 +61,7 @@ Pyramid make_pyramid(int h, int w) {
 }
 
 struct WaveAcc {                 // per slice (position in sel)
-    double energy[MAXL + 1][3];  // sum of float32 squares per detail band (ad, da, dd)
+    float energy[MAXL + 1][3];   // np.sum(d*d) per detail band (ad, da, dd): float32, numpy's pairwise order
     double thr[MAXL + 1][3];     // BayesShrink thresholds
     double sigma;
     unsigned dd_zero;
@@ -72,7 +78,6 @@ k_haar_fwd(const float* __restrict__ in, long long in_stride, int h0, int w0, Di
            float* __restrict__ det, long long det_stride, long long det_off,
            WaveAcc* __restrict__ acc, unsigned* __restrict__ l1, int want_hist) {
     __shared__ unsigned hh[SEL_L1_BINS];
-    __shared__ double red[3 * 32];
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
     if (skip && skip[s]) return;
@@ -85,7 +90,6 @@ k_haar_fwd(const float* __restrict__ in, long long in_stride, int h0, int w0, Di
     const bool hist = FIRST && want_hist;
     if (hist) for (int i = threadIdx.x; i < SEL_L1_BINS; i += NT) hh[i] = 0;
     if (hist) __syncthreads();
-    double e[3] = {0.0, 0.0, 0.0};
     unsigned nz = 0;
     const long long total = band;
     for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
@@ -108,22 +112,13 @@ k_haar_fwd(const float* __restrict__ in, long long in_stride, int h0, int w0, Di
         db[i] = ad;
         db[band + i] = da;
         db[2 * band + i] = dd;
-        e[0] += (double)__fmul_rn(ad, ad);
-        e[1] += (double)__fmul_rn(da, da);
-        e[2] += (double)__fmul_rn(dd, dd);
         if (hist) {
             const float a = fabsf(dd);
             nz += (a == 0.0f);
             atomicAdd(&hh[f2key(a) >> 21], 1u);
         }
     }
-    block_sum<3>(e, red);
     WaveAcc* A = acc + si;
-    if (threadIdx.x == 0) {
-        atomicAdd(&A->energy[level][0], e[0]);
-        atomicAdd(&A->energy[level][1], e[1]);
-        atomicAdd(&A->energy[level][2], e[2]);
-    }
     if (hist) {
         nz = warp_sum_u(nz);
         if ((threadIdx.x & 31) == 0 && nz) atomicAdd(&A->dd_zero, nz);
@@ -131,6 +126,116 @@ k_haar_fwd(const float* __restrict__ in, long long in_stride, int h0, int w0, Di
         unsigned* g = l1 + (size_t)si * SEL_L1_BINS;
         for (int i = threadIdx.x; i < SEL_L1_BINS; i += NT) { unsigned v = hh[i]; if (v) atomicAdd(&g[i], v); }
     }
+}
+
+// ---- np.sum(d*d) in numpy's exact float32 pairwise order ---------------------------------------
+// numpy reduces a contiguous float32 array with pairwise_sum: blocks of <= 128 elements are summed
+// with 8 interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a
+// sequential tail; larger ranges split at n/2 rounded down to a multiple of 8 and add the halves.
+// The BayesShrink threshold depends on these float32 sums, and a 1-ulp change of a threshold can
+// move a pixel across a CLAHE bin edge downstream, so the order is reproduced exactly: a leaf
+// table and a post-order combine program are built on the host for each band length.
+struct PwLeaf { int level; int off; int len; };          // off: element offset inside the band
+struct PwLevel { int leaf0; int n_leaf; int prog0; int n_prog; long long det_off; long long band; };
+
+struct PwPlan {
+    std::vector<PwLeaf> leaves;
+    std::vector<unsigned char> prog;       // 0 = push next leaf sum, 1 = pop two, push their sum
+    std::vector<PwLevel> levels;           // index 0 unused
+    int max_depth = 0;
+};
+
+void pw_build(int off, int n, int level, PwPlan& p, int depth) {
+    if (depth > p.max_depth) p.max_depth = depth;
+    if (n <= 128) {
+        p.leaves.push_back({level, off, n});
+        p.prog.push_back(0);
+        return;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    pw_build(off, n2, level, p, depth + 1);
+    pw_build(off + n2, n - n2, level, p, depth + 1);
+    p.prog.push_back(1);
+}
+
+PwPlan make_pw_plan(const Pyramid& py) {
+    PwPlan p;
+    p.levels.resize(py.L + 1);
+    for (int l = 1; l <= py.L; ++l) {
+        PwLevel& lv = p.levels[l];
+        lv.leaf0 = (int)p.leaves.size();
+        lv.prog0 = (int)p.prog.size();
+        lv.band = (long long)py.H[l] * py.W[l];
+        lv.det_off = py.off[l];
+        pw_build(0, (int)lv.band, l, p, 1);
+        lv.n_leaf = (int)p.leaves.size() - lv.leaf0;
+        lv.n_prog = (int)p.prog.size() - lv.prog0;
+    }
+    return p;
+}
+
+const PwPlan& cached_pw_plan(const Pyramid& py) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, std::unique_ptr<PwPlan>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(py.H[0], py.W[0]);
+    auto it = cache.find(key);
+    if (it == cache.end()) it = cache.emplace(key, std::make_unique<PwPlan>(make_pw_plan(py))).first;
+    return *it->second;
+}
+
+// 8 lanes per leaf (lane j = numpy's accumulator r[j]); grid.y = slice, grid.z = band.
+__global__ void __launch_bounds__(NT)
+k_pw_leaves(const float* __restrict__ det, long long det_stride, const PwLeaf* __restrict__ leaves,
+            const PwLevel* __restrict__ levels, int n_leaves, Dims d, const int* __restrict__ skip,
+            float* __restrict__ leaf_sums) {
+    const int si = blockIdx.y, b = blockIdx.z;
+    if (skip && skip[slice_of(d.sel, si)]) return;
+    const int g = (blockIdx.x * NT + threadIdx.x) >> 3, j = threadIdx.x & 7;
+    if (g >= n_leaves) return;                      // whole 8-lane groups leave together
+    const PwLeaf lf = leaves[g];
+    const PwLevel lv = levels[lf.level];
+    const float* a = det + (size_t)si * det_stride + lv.det_off + (size_t)b * lv.band + lf.off;
+    const int n = lf.len;
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
+    float res;
+    if (n < 8) {
+        res = 0.0f;
+        if (j == 0) for (int i = 0; i < n; ++i) { const float v = a[i]; res = __fadd_rn(res, __fmul_rn(v, v)); }
+    } else {
+        float v = a[j];
+        float r = __fmul_rn(v, v);
+        const int n8 = n - (n & 7);
+        for (int i = 8; i < n8; i += 8) { v = a[i + j]; r = __fadd_rn(r, __fmul_rn(v, v)); }
+        r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1));     // r0+r1, r2+r3, ...
+        r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 2));     // (r0+r1)+(r2+r3), ...
+        r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+        res = r;
+        if (j == 0) for (int i = n8; i < n; ++i) { v = a[i]; res = __fadd_rn(res, __fmul_rn(v, v)); }
+    }
+    if (j == 0) leaf_sums[((size_t)si * 3 + b) * n_leaves + g] = res;
+}
+
+// One thread per (slice, level, band) replays the post-order combine program.
+__global__ void k_pw_combine(const unsigned char* __restrict__ prog, const PwLevel* __restrict__ levels,
+                             int L, int n_leaves, Dims d, const int* __restrict__ skip,
+                             const float* __restrict__ leaf_sums, WaveAcc* __restrict__ acc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.n_sel * L * 3) return;
+    const int si = t / (L * 3), rem = t - si * L * 3;
+    const int l = rem / 3 + 1, b = rem - (l - 1) * 3;
+    if (skip && skip[slice_of(d.sel, si)]) return;
+    const PwLevel lv = levels[l];
+    const float* ls = leaf_sums + ((size_t)si * 3 + b) * n_leaves + lv.leaf0;
+    const unsigned char* pg = prog + lv.prog0;
+    float stack[40];
+    int sp = 0, next = 0;
+    for (int i = 0; i < lv.n_prog; ++i) {
+        if (pg[i] == 0) stack[sp++] = ls[next++];
+        else { --sp; stack[sp - 1] = __fadd_rn(stack[sp - 1], stack[sp]); }
+    }
+    acc[si].energy[l][b] = stack[0];
 }
 
 __global__ void k_wave_ranks(Dims d, int len, const WaveAcc* __restrict__ acc, int* __restrict__ ranks) {
@@ -162,7 +267,7 @@ __global__ void k_wave_thresholds(Dims d, Pyramid p, WaveAcc* __restrict__ acc,
         for (int l = 1; l <= p.L; ++l) {
             const double cnt = (double)p.H[l] * (double)p.W[l];
             for (int b = 0; b < 3; ++b) {
-                const float dvar = (float)(A.energy[l][b] / cnt);     // np.mean of float32 squares
+                const float dvar = __fdiv_rn(A.energy[l][b], (float)cnt);   // np.mean: float32 sum / count
                 const double diff = (double)dvar - var;               // float32 - float64 -> float64
                 double root;
                 if (diff >= (double)eps) root = sqrt(diff);           // max(diff, eps) keeps `diff` on ties
@@ -180,7 +285,7 @@ __global__ void k_wave_thresholds(Dims d, Pyramid p, WaveAcc* __restrict__ acc,
         for (int l = 1; l <= p.L; ++l) {
             const double cnt = (double)p.H[l] * (double)p.W[l];
             for (int b = 0; b < 3; ++b) {
-                const float dvar = (float)(A.energy[l][b] / cnt);
+                const float dvar = __fdiv_rn(A.energy[l][b], (float)cnt);
                 float diff = __fsub_rn(dvar, varf);
                 float m = diff >= eps ? diff : (diff != diff ? diff : eps);
                 A.thr[l][b] = (double)__fdiv_rn(varf, __fsqrt_rn(m));
@@ -282,7 +387,15 @@ k_haar_inv(const TA* __restrict__ ain, long long a_stride, int a_pitch, int hd, 
 struct WaveBufs {
     WaveAcc* acc; float* det; float* a0; float* a1; double* r0; double* r1;
     unsigned* l1; int* ranks; float* med; void* sel_ws; size_t sel_ws_bytes;
+    PwLeaf* pw_leaves; PwLevel* pw_levels; unsigned char* pw_prog; float* pw_sums;
 };
+
+// upper bounds that depend only on the pyramid (the plan itself is built per call)
+inline size_t pw_max_leaves(const Pyramid& p) {
+    size_t n = 0;
+    for (int l = 1; l <= p.L; ++l) n += (size_t)p.H[l] * p.W[l] / 32 + 2;   // leaves hold > 64 elements, except tiny bands
+    return n;
+}
 
 void carve(Arena& a, int n, int n_sel, const Pyramid& p, WaveBufs& b) {
     b.acc = a.take<WaveAcc>(n_sel);
@@ -296,6 +409,11 @@ void carve(Arena& a, int n, int n_sel, const Pyramid& p, WaveBufs& b) {
     b.med = a.take<float>((size_t)n * 2);
     b.sel_ws_bytes = select_workspace_bytes(n_sel);
     b.sel_ws = a.take<char>(b.sel_ws_bytes);
+    const size_t ml = pw_max_leaves(p);
+    b.pw_leaves = a.take<PwLeaf>(ml);
+    b.pw_levels = a.take<PwLevel>(MAXL + 2);
+    b.pw_prog = a.take<unsigned char>(2 * ml + 16);
+    b.pw_sums = a.take<float>((size_t)n_sel * 3 * ml);
 }
 
 inline int grid_x(long long items) {
@@ -375,6 +493,21 @@ int wavelet_denoise_run(const float* in, float* out, const Dims& d, int mode_har
                                                        b.det, p.det_per_slice, p.off[l], b.acc, b.l1, 0);
     }
     const float* coarse = abuf[(p.L - 1) & 1];
+
+    // ---- band energies np.sum(d*d) in numpy's pairwise order ----
+    {
+        const PwPlan& plan = cached_pw_plan(p);      // process-lifetime host copy: safe source for async copies
+        const int n_leaves = (int)plan.leaves.size();
+        if ((size_t)n_leaves > pw_max_leaves(p) || plan.max_depth > 38)
+            return set_error(MDIMG_ERR_INVALID, "wavelet: pairwise plan exceeds its bounds (%d leaves, depth %d)", n_leaves, plan.max_depth);
+        cudaMemcpyAsync(b.pw_leaves, plan.leaves.data(), sizeof(PwLeaf) * n_leaves, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(b.pw_levels, plan.levels.data(), sizeof(PwLevel) * plan.levels.size(), cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(b.pw_prog, plan.prog.data(), plan.prog.size(), cudaMemcpyHostToDevice, stream);
+        dim3 lgrid((n_leaves * 8 + NT - 1) / NT, d.n_sel, 3);
+        MDIMG_LAUNCH k_pw_leaves<<<lgrid, NT, 0, stream>>>(b.det, p.det_per_slice, b.pw_leaves, b.pw_levels, n_leaves, d, skip, b.pw_sums);
+        const int nt = d.n_sel * p.L * 3;
+        MDIMG_LAUNCH k_pw_combine<<<(nt + 127) / 128, 128, 0, stream>>>(b.pw_prog, b.pw_levels, p.L, n_leaves, d, skip, b.pw_sums, b.acc);
+    }
 
     // ---- sigma (finest 'dd' band) and thresholds ----
     if (want_hist) {

@@ -307,8 +307,17 @@ def run_gpu(args) -> None:
         bytes_per_launch = 20.0 * chunk * H * W          # per loop body
         achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9
         tv_iters = last.tv_iterations
+        traffic = None
+        tj = ROOT / "profiles" / "r01_tv_pair_traffic.json"
+        if tj.exists():
+            try:
+                traffic = float(json.loads(tj.read_text())["dram_bytes_per_pixel_per_body"]) * chunk * H * W
+            except Exception:  # noqa: BLE001
+                traffic = None
         roof = {"bound": "hbm", "kernel": "k_tv_pair", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per pixel and body "
+                                  "(profiles/r01_tv_pair_traffic.json) x pixels of this launch",
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "launch_ms": per_launch_ms,
                 "note": f"per loop body: 20 B/px (x 4 + p 8 read, p 8 written) x {chunk} slices x 512x512; one "

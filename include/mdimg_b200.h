@@ -87,6 +87,13 @@ int mdimg_normalize_u16(const uint16_t* in, float* out, int n, int h, int w, con
                         int n_sel, void* ws, size_t ws_bytes, void* stream);
 int mdimg_normalize_f32(const float* in, float* out, int n, int h, int w, const int32_t* sel,
                         int n_sel, void* ws, size_t ws_bytes, void* stream);
+/* The pixel path of load_dicom (pipeline/dicom_io.py:44-49) fused with normalize_image: pydicom's
+ * modality rescale float32(float64(raw) * slope + intercept) when has_rescale, `image.max() - image`
+ * over the whole stack when monochrome1, then per-slice normalisation.  raw: 16-bit samples
+ * (is_signed selects int16).  Workspace: MDIMG_OP_NORMALIZE. */
+int mdimg_ingest_u16(const uint16_t* raw, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                     double slope, double intercept, int has_rescale, int monochrome1, int is_signed,
+                     void* ws, size_t ws_bytes, void* stream);
 
 /* ---- metrics ----------------------------------------------------------------------------- */
 /* compute_metrics (pipeline/metrics.py:42-109) for every slice; flags bit0 additionally fills

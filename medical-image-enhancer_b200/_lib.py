@@ -40,6 +40,7 @@ PROTOTYPES = {
     "mdimg_minmax_f32": (_i, [_p, *_IMG, _p, *_WS]),
     "mdimg_normalize_u16": (_i, [_p, _p, *_IMG, *_WS]),
     "mdimg_normalize_f32": (_i, [_p, _p, *_IMG, *_WS]),
+    "mdimg_ingest_u16": (_i, [_p, _p, *_IMG, _d, _d, _i, _i, _i, *_WS]),
     "mdimg_metrics": (_i, [_p, *_IMG, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                            C.POINTER(C.c_float), _p, *_WS]),
     "mdimg_estimate_sigma": (_i, [_p, *_IMG, _p, *_WS]),

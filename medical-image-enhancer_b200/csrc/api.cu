@@ -109,7 +109,7 @@ size_t mdimg_workspace_bytes(int op, int n, int h, int w, int param) {
     if (n < 1) n = 1;
     switch (op) {
         case MDIMG_OP_NORMALIZE:
-        case MDIMG_OP_MINMAX: return mm_bytes(n);
+        case MDIMG_OP_MINMAX: return mm_bytes(n) + 256;
         case MDIMG_OP_METRICS: return metrics_workspace_bytes(n, h, w);
         case MDIMG_OP_SIGMA: return sigma_workspace_bytes(n, h, w);
         case MDIMG_OP_QUALITY: return quality_workspace_bytes(n, h, w);
@@ -152,6 +152,18 @@ int mdimg_normalize_u16(const uint16_t* in, float* out, int n, int h, int w, con
     int rc = minmax_u16_run(in, d, mm, (cudaStream_t)stream);
     if (rc) return rc;
     return normalize_u16_run(in, out, d, mm, (cudaStream_t)stream);
+}
+
+int mdimg_ingest_u16(const uint16_t* raw, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                     double slope, double intercept, int has_rescale, int monochrome1, int is_signed,
+                     void* ws, size_t ws_bytes, void* stream) {
+    if (bad_dims(n, h, w, sel, n_sel)) return MDIMG_ERR_INVALID;
+    Dims d = make_dims(n, h, w, sel, n_sel);
+    Arena a(ws, ws_bytes);
+    uint2* mm = a.take<uint2>(n);
+    uint2* gmm = a.take<uint2>(1);
+    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "ingest: workspace too small");
+    return ingest_run(raw, out, d, slope, intercept, has_rescale, monochrome1, is_signed, mm, gmm, (cudaStream_t)stream);
 }
 
 int mdimg_normalize_f32(const float* in, float* out, int n, int h, int w, const int32_t* sel,

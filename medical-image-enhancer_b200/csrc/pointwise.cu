@@ -136,6 +136,66 @@ k_normalize_u16(const uint16_t* __restrict__ in, float* __restrict__ out, Dims d
     }
 }
 
+// ---- ingestion: modality rescale + MONOCHROME1 inversion + normalize_image in one pass --------
+// load_dicom (pipeline/dicom_io.py:44-49): v = float32(float64(raw) * slope + intercept) (pydicom's
+// apply_modality_lut), then `image.max() - image` for MONOCHROME1 (max over the whole pixel array,
+// i.e. all frames), then normalize_image per 2-D frame (dicom_io.py:84-91).  All three maps are
+// monotone in the raw value, so every min / max follows from the raw per-slice and global extrema.
+struct IngestParams { double slope, intercept; int has_rescale, invert, is_signed; };
+
+__device__ __forceinline__ float ingest_value(float raw, const IngestParams& P) {
+    if (!P.has_rescale) return raw;
+    return (float)__dadd_rn(__dmul_rn((double)raw, P.slope), P.intercept);
+}
+
+__global__ void k_global_mm(int n_sel, Dims d, const uint2* __restrict__ mm, uint2* __restrict__ gmm) {
+    // one block: extrema over the selected slices (keys are order preserving)
+    __shared__ unsigned smin[32], smax[32];
+    unsigned lo = 0xFFFFFFFFu, hi = 0u;
+    for (int si = threadIdx.x; si < n_sel; si += blockDim.x) {
+        const uint2 v = mm[slice_of(d.sel, si)];
+        lo = min(lo, v.x);
+        hi = max(hi, v.y);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { smin[wid] = lo; smax[wid] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = min(lo, smin[w]); hi = max(hi, smax[w]); }
+        gmm[0] = make_uint2(lo, hi);
+    }
+}
+
+__global__ void __launch_bounds__(NT)
+k_ingest(const uint16_t* __restrict__ in, float* __restrict__ out, Dims d, const uint2* __restrict__ mm,
+         const uint2* __restrict__ gmm, IngestParams P) {
+    const int s = slice_of(d.sel, blockIdx.y);
+    const float rmin = key2f(mm[s].x), rmax = key2f(mm[s].y);
+    const bool inc = !P.has_rescale || P.slope >= 0.0;
+    float vmin = ingest_value(inc ? rmin : rmax, P), vmax = ingest_value(inc ? rmax : rmin, P);
+    float M = 0.0f;
+    if (P.invert) {
+        M = ingest_value(inc ? key2f(gmm[0].y) : key2f(gmm[0].x), P);     // image.max() over all frames
+        const float nmin = __fsub_rn(M, vmax), nmax = __fsub_rn(M, vmin);
+        vmin = nmin; vmax = nmax;
+    }
+    const double span = (double)vmax - (double)vmin;
+    const bool zero = span < 1e-8;
+    const float lo = vmin, denom = (float)span;
+    const long long len = d.px();
+    const uint16_t* p = in + (size_t)s * len;
+    float* o = out + (size_t)s * len;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < len; i += (long long)gridDim.x * NT) {
+        const uint16_t u = p[i];
+        const float raw = P.is_signed ? (float)(short)u : (float)u;
+        float v = ingest_value(raw, P);
+        if (P.invert) v = __fsub_rn(M, v);
+        o[i] = zero ? 0.0f : __fdiv_rn(__fsub_rn(v, lo), denom);
+    }
+}
+
 struct GammaF {
     const uint2* mm; int* neg_flag; double gamma;
     __device__ bool prepare(int s) {
@@ -202,6 +262,21 @@ int minmax_u16_run(const uint16_t* img, const Dims& d, uint2* mm, cudaStream_t s
     MDIMG_LAUNCH k_mm_init<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, mm);
     MDIMG_LAUNCH k_minmax<uint16_t><<<dim3(blocks_for(d.px(), 16), d.n_sel), NT, 0, stream>>>(img, d, mm);
     return check_launch("minmax_u16");
+}
+
+int ingest_run(const uint16_t* in, float* out, const Dims& d, double slope, double intercept,
+               int has_rescale, int invert, int is_signed, uint2* mm, uint2* gmm, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    MDIMG_LAUNCH k_mm_init<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, mm);
+    if (is_signed)
+        MDIMG_LAUNCH k_minmax<short><<<dim3(blocks_for(d.px(), 16), d.n_sel), NT, 0, stream>>>((const short*)in, d, mm);
+    else
+        MDIMG_LAUNCH k_minmax<uint16_t><<<dim3(blocks_for(d.px(), 16), d.n_sel), NT, 0, stream>>>(in, d, mm);
+    MDIMG_LAUNCH k_global_mm<<<1, 256, 0, stream>>>(d.n_sel, d, mm, gmm);
+    IngestParams P;
+    P.slope = slope; P.intercept = intercept; P.has_rescale = has_rescale; P.invert = invert; P.is_signed = is_signed;
+    MDIMG_LAUNCH k_ingest<<<dim3(blocks_for(d.px(), 8), d.n_sel), NT, 0, stream>>>(in, out, d, mm, gmm, P);
+    return check_launch("ingest");
 }
 
 int minmax_decode_run(const uint2* mm, const Dims& d, float* out2, cudaStream_t stream) {

@@ -22,3 +22,21 @@ def normalize_image(image: np.ndarray) -> np.ndarray:
         dev = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(ops.device)
     out = ops.normalize(dev[None])
     return out[0].cpu().numpy()
+
+
+def ingest_stack(raw: np.ndarray, slope=None, intercept=None, monochrome1: bool = False) -> np.ndarray:
+    """Pixel path of the reference's ``load_dicom`` (pipeline/dicom_io.py:44-49) fused with
+    ``normalize_image`` for every frame of a 16-bit stack: modality rescale
+    ``float32(float64(raw) * slope + intercept)``, MONOCHROME1 inversion against the maximum of the
+    whole pixel array, per-frame normalisation to [0, 1].  Unlike the reference, which keeps only
+    the middle frame of a multi-frame object (dicom_io.py:72-73), every frame is returned."""
+    arr = np.asarray(raw)
+    if arr.dtype not in (np.uint16, np.int16):
+        raise ValueError("ingest_stack expects int16 or uint16 samples")
+    if arr.ndim == 2:
+        arr = arr[None]
+    ops = get_ops()
+    dev = torch.from_numpy(np.ascontiguousarray(arr).view(np.int16)).to(ops.device)
+    if arr.dtype == np.uint16:
+        dev = dev.view(torch.uint16)
+    return ops.ingest(dev, slope, intercept, monochrome1).cpu().numpy()

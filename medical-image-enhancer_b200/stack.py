@@ -142,6 +142,24 @@ class StackOps:
         self._call(fn, self._ptr(src), self._ptr(out), n, h, w, C.c_void_p(0), 0, ws, wsb, self._stream())
         return out
 
+    def ingest(self, raw: torch.Tensor, slope: Optional[float] = None, intercept: Optional[float] = None,
+               monochrome1: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """load_dicom's pixel path fused with normalize_image for a stack of 16-bit frames
+        (pipeline/dicom_io.py:44-49,84-91): modality rescale (when slope/intercept are given),
+        MONOCHROME1 inversion against the stack maximum, per-slice normalisation."""
+        if raw.dtype not in (torch.int16, torch.uint16):
+            raise ValueError("ingest expects 16-bit raw samples (int16 or uint16)")
+        src = self._img(raw, raw.dtype)
+        n, h, w = src.shape
+        if out is None:
+            out = torch.empty((n, h, w), dtype=torch.float32, device=self.device)
+        has = slope is not None and intercept is not None
+        ws, wsb = self._ws_for(_lib.OP_NORMALIZE, n, h, w)
+        self._call(self.lib.mdimg_ingest_u16, self._ptr(src), self._ptr(out), n, h, w, C.c_void_p(0), 0,
+                   float(slope) if has else 1.0, float(intercept) if has else 0.0, 1 if has else 0,
+                   1 if monochrome1 else 0, 1 if raw.dtype == torch.int16 else 0, ws, wsb, self._stream())
+        return out
+
     def minmax(self, img: torch.Tensor, sel=None) -> torch.Tensor:
         n, h, w = self._img(img).shape
         out = torch.zeros((n, 2), dtype=torch.float32, device=self.device)

@@ -237,3 +237,20 @@ def compute_objective_score(validation: dict) -> Tuple[float, dict]:
     breakdown = {k: round(v, 4) for k, v in parts.items()}
     breakdown["passes"] = passes
     return round(float(score), 4), breakdown
+
+
+def ingest_frames(raw: np.ndarray, slope=None, intercept=None, monochrome1: bool = False) -> np.ndarray:
+    """Pixel path of ``load_dicom`` (pipeline/dicom_io.py:44-49) followed by ``normalize_image`` on
+    every frame: pydicom's ``apply_modality_lut`` rescale (float64 multiply, float64 add — pydicom is
+    an un-vendored dependency, restated from pydicom/pixel_data_handlers/util.py; PARITY UNPINNED),
+    ``.astype(float32)``, ``image.max() - image`` over the whole array for MONOCHROME1."""
+    arr = raw
+    if slope is not None and intercept is not None:
+        arr = arr.astype(np.float64) * float(slope)
+        arr += float(intercept)
+    img = arr.astype(np.float32)
+    if monochrome1:
+        img = img.max() - img
+    if img.ndim == 2:
+        return normalize_image(img)
+    return np.stack([normalize_image(f) for f in img])

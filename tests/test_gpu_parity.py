@@ -258,3 +258,18 @@ def test_kernel_launches_are_counted(ops, dev, images):
     before = ops.lib.mdimg_launch_count()
     ops.metrics(dev(images["noisy64"]))
     assert ops.lib.mdimg_launch_count() - before >= 10
+
+
+# ------------------------------------------------------------------ ingestion
+@pytest.mark.parametrize("dtype,slope,intercept,mono1", [
+    (np.uint16, None, None, False), (np.uint16, 1.0, -1024.0, False), (np.int16, 1.0, -1024.0, True),
+    (np.uint16, 0.25, 3.5, True), (np.int16, -2.0, 100.0, False), (np.uint16, None, None, True)])
+def test_ingest_matches_load_dicom_pixel_path(ops, synth, dtype, slope, intercept, mono1):
+    from mdimg_b200.pipeline.dicom_io import ingest_stack
+    raw = np.stack([synth.ct_slice(1000 + z, z / 5, size=128) for z in range(5)])
+    if dtype == np.int16:
+        raw = (raw.astype(np.int32) - 1500).astype(np.int16)
+    got = ingest_stack(raw.astype(dtype), slope, intercept, mono1)
+    ref = omet.ingest_frames(raw.astype(dtype), slope, intercept, mono1)
+    np.testing.assert_array_equal(got, ref)
+    assert got.min() == 0.0 and got.max() == 1.0

@@ -233,3 +233,40 @@ def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
     main.synchronize()
     res = StackResult(enhanced=None, packed=packed_host.numpy().copy(), labels=labels)
     return out_t.numpy(), res
+
+
+def score_plans(images: torch.Tensor, plans, ops: Optional[StackOps] = None):
+    """Tuning-loop batch (reference: pipeline/tools.py:95-183 called once per
+    candidate and image by the LLM tuner): evaluate K candidate plans on N normalised images.
+    The metrics of the originals are computed once and shared by every candidate; each candidate is
+    one stack-wide enhancement + metrics + SSIM/PSNR pass.  Returns (scores [K, N] float64,
+    results: list of K StackResult without pixels)."""
+    ops = ops or get_ops(images.device)
+    if images.dtype != torch.float32:
+        raise ValueError("score_plans expects a float32 [N, H, W] stack normalised to [0, 1]")
+    eng = Engine(ops)
+    n = images.shape[0]
+    rows_b = ops.metrics(images, with_niqe=True)
+    scores = np.zeros((len(plans), n), np.float64)
+    results = []
+    for k, plan in enumerate(plans):
+        res = eng.enhance_from_params(images, plan, rows_before=rows_b, on_error="flag")
+        fr = ops.fullref(images, res.image)
+        packed = torch.zeros((n, PACK_COLS), dtype=torch.float64, device=ops.device)
+        packed[:, :ROW_COLS] = rows_b
+        packed[:, ROW_COLS:2 * ROW_COLS] = res.rows_after
+        packed[:, 2 * ROW_COLS:2 * ROW_COLS + 2] = fr
+        host = packed.cpu().numpy()
+        host[:, 2 * ROW_COLS + 2] = res.halo
+        host[:, 2 * ROW_COLS + 3] = res.noise_guard
+        host[:, 2 * ROW_COLS + 4] = res.over_processed
+        if res.tv_iterations is not None:
+            host[:, 2 * ROW_COLS + 5] = res.tv_iterations
+        for i in res.errors:
+            host[i, 2 * ROW_COLS + 6] = 1.0
+        sr = StackResult(enhanced=None, packed=host, labels=res.labels)
+        for i in range(n):
+            # tool_score_plan returns -100 when validation failed with an error (tools.py:173-174)
+            scores[k, i] = -100.0 if sr.failed[i] else sr.score(i)[0]
+        results.append(sr)
+    return scores, results

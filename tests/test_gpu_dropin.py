@@ -229,3 +229,26 @@ def test_stack_pipeline_matches_per_slice_calls(ops, synth):
         assert v["ssim"] == pytest.approx(refv["ssim"], rel=1e-6)
         assert v["metrics_after"]["entropy"] == pytest.approx(refv["metrics_after"]["entropy"], rel=1e-9)
         assert isinstance(res.score(z)[0], float)
+
+
+def test_score_plans_matches_the_tool_loop(ops, images, synth):
+    """K candidate plans x N images (pipeline/tools.py:95-183 semantics) vs the oracle run one by one."""
+    import torch
+    from mdimg_b200.batch import score_plans
+    from mdimg_b200.pipeline.schemas import EnhancementParams, EnhancementPlan
+    names = ["noisy64", "clean64", "lowc64"]
+    stack = torch.from_numpy(np.stack([images[k] for k in names])).to(ops.device)
+    plans = [
+        EnhancementPlan(recommended_ops=["denoise", "clahe"], params=EnhancementParams(clahe_clip_limit=0.01)),
+        EnhancementPlan(recommended_ops=["unsharp", "gamma"], params=EnhancementParams(gamma=1.2, unsharp_amount=2.0)),
+        EnhancementPlan(recommended_ops=["tv_denoise", "bilateral"],
+                        params=EnhancementParams(tv_denoise_weight=0.08, bilateral_d=3)),
+    ]
+    scores, results = score_plans(stack, plans, ops=ops)
+    assert scores.shape == (3, 3)
+    for k, plan in enumerate(plans):
+        for i, name in enumerate(names):
+            ref_img, ref_labels = oenh.apply_enhancements_from_params(images[name], plan)
+            ref_score, _ = omet.compute_objective_score(omet.compute_validation(images[name], ref_img))
+            assert results[k].labels[i] == ref_labels
+            assert scores[k, i] == pytest.approx(ref_score, abs=5e-4), (k, name)

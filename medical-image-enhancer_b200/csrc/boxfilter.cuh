@@ -115,4 +115,65 @@ __device__ __forceinline__ void box_horizontal(double* const (&V)[NQ], double in
     }
 }
 
+// ---- float32-storage variants -------------------------------------------------------------------
+// Same arithmetic (double running sums, float32 rounding between the passes), but the tiles are
+// kept as float32 in shared memory and converted when they enter / leave a window: a quarter of
+// the shared memory of the double tiles, i.e. 4-6 CTAs per SM instead of 2 for these
+// latency-bound kernels, for ~50 % more conversion instructions.
+
+// Axis-0 pass of x and x*x (float32 product, as numpy's image**2) from a float tile.
+template <int K>
+__device__ __forceinline__ void box_vertical_xq(const float* X, float* VS, float* VQ, double inv) {
+    typedef BoxTile<K> T;
+    const int item = threadIdx.x;
+    if (item < T::XW * T::NSEG) {
+        const int sg = item / T::XW, c = item - sg * T::XW;
+        const int r0 = sg * T::RS;
+        const int r1 = min(r0 + T::RS, T::TH);
+        double s = 0.0, q = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float v = X[(r0 + k) * T::XP + c];
+            s += (double)v;
+            q += (double)__fmul_rn(v, v);
+        }
+        for (int r = r0; r < r1; ++r) {
+            VS[r * T::XP + c] = (float)(s * inv);
+            VQ[r * T::XP + c] = (float)(q * inv);
+            if (r + 1 < r1) {
+                const float vn = X[(r + K) * T::XP + c], vo = X[r * T::XP + c];
+                s += (double)vn - (double)vo;
+                q += (double)__fmul_rn(vn, vn) - (double)__fmul_rn(vo, vo);
+            }
+        }
+    }
+}
+
+// Axis-1 pass over float32 V tiles: f(r, c, m[NQ]) for the 8 pixels of (lane = row, warp = segment).
+template <int K, int NQ, typename F>
+__device__ __forceinline__ void box_horizontal_f(float* const (&V)[NQ], double inv, F&& f) {
+    typedef BoxTile<K> T;
+    const int r = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int c0 = seg * 8;
+    double s[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        s[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) s[q] += (double)V[q][r * T::XP + c0 + k];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float m[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) m[q] = (float)(s[q] * inv);
+        f(r, c0 + j, m);
+        if (j < 7) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                s[q] += (double)V[q][r * T::XP + c0 + j + K] - (double)V[q][r * T::XP + c0 + j];
+        }
+    }
+}
+
 }  // namespace mdimg

@@ -20,10 +20,9 @@ typedef BoxTile<16> B16;
 constexpr int B16L = 8;   // window [i-8, i+7]
 
 struct Box16Smem {
-    double X[B16::XH * B16::XP];
-    double Q[B16::XH * B16::XP];
-    double VS[B16::TH * B16::XP];
-    double VQ[B16::TH * B16::XP];
+    float X[B16::XH * B16::XP];
+    float VS[B16::TH * B16::XP];
+    float VQ[B16::TH * B16::XP];
     double red[2 * 32];
 };
 
@@ -39,21 +38,14 @@ k_box16_stats(const float* __restrict__ img, Dims d, double* __restrict__ acc2) 
     const int x0 = tx * TW, y0 = ty * TH;
     const float* src = img + (size_t)s * d.h * d.w;
     const int tid = threadIdx.x;
-    load_tile<XW, XH, B16L, 0>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) {
-        sm.X[r * XP + c] = (double)v;
-        sm.Q[r * XP + c] = (double)__fmul_rn(v, v);
-    });
+    load_tile<XW, XH, B16L, 0>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) { sm.X[r * XP + c] = v; });
     __syncthreads();
-    {
-        double* const xin[2] = {sm.X, sm.Q};
-        double* const vout[2] = {sm.VS, sm.VQ};
-        box_vertical<16, 2>(xin, vout, 0.0625);
-    }
+    box_vertical_xq<16>(sm.X, sm.VS, sm.VQ, 0.0625);
     __syncthreads();
     double v[2] = {0.0, 0.0};
     {
-        double* const vin[2] = {sm.VS, sm.VQ};
-        box_horizontal<16, 2>(vin, 0.0625, [&](int r, int c, const float (&m)[2]) {
+        float* const vin[2] = {sm.VS, sm.VQ};
+        box_horizontal_f<16, 2>(vin, 0.0625, [&](int r, int c, const float (&m)[2]) {
             if (y0 + r < d.h && x0 + c < d.w) {
                 const double lv = (double)fmaxf(__fsub_rn(m[1], __fmul_rn(m[0], m[0])), 0.0f);
                 v[0] += lv;
@@ -75,7 +67,7 @@ constexpr int HALO = 3;
 struct SsimSmem {
     float A[B7::XH * B7::XP];
     float B[B7::XH * B7::XP];
-    double V[5][B7::TH * B7::XP];   // axis-0 means of a, b, a*a, b*b, a*b
+    float V[5][B7::TH * B7::XP];    // axis-0 means of a, b, a*a, b*b, a*b (float32, as scipy stores them)
     double red[2 * 32];
 };
 
@@ -115,7 +107,7 @@ k_ssim_psnr(const float* __restrict__ ia, const float* __restrict__ ib, Dims d,
         for (int k = 0; k < 7; ++k) add(r0 + k, 1.0);
         for (int r = r0; r < r1; ++r) {
 #pragma unroll
-            for (int q = 0; q < 5; ++q) sm.V[q][r * XP + c] = round32(sum[q] * inv7);
+            for (int q = 0; q < 5; ++q) sm.V[q][r * XP + c] = (float)(sum[q] * inv7);
             if (r + 1 < r1) { add(r + 7, 1.0); add(r, -1.0); }
         }
     }
@@ -124,8 +116,8 @@ k_ssim_psnr(const float* __restrict__ ia, const float* __restrict__ ib, Dims d,
     const float C1 = (float)1.0e-4, C2 = (float)9.0e-4;
     double v[2] = {0.0, 0.0};   // sum S over the crop, sum (a-b)^2 over the image
     {
-        double* const vin[5] = {sm.V[0], sm.V[1], sm.V[2], sm.V[3], sm.V[4]};
-        box_horizontal<7, 5>(vin, inv7, [&](int r, int c, const float (&m)[5]) {
+        float* const vin[5] = {sm.V[0], sm.V[1], sm.V[2], sm.V[3], sm.V[4]};
+        box_horizontal_f<7, 5>(vin, inv7, [&](int r, int c, const float (&m)[5]) {
             const int gy = y0 + r, gx = x0 + c;
             if (gy < d.h && gx < d.w) {
                 const float a = sm.A[(r + HALO) * XP + c + HALO], b = sm.B[(r + HALO) * XP + c + HALO];

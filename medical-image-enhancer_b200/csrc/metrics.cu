@@ -62,10 +62,9 @@ __device__ __forceinline__ float lerp_np(float a, float b, float t) {
 typedef BoxTile<7> B7;
 
 struct StencilSmem {
-    double X[B7::XH * B7::XP];
-    double Q[B7::XH * B7::XP];
-    double VS[B7::TH * B7::XP];
-    double VQ[B7::TH * B7::XP];
+    float X[B7::XH * B7::XP];
+    float VS[B7::TH * B7::XP];
+    float VQ[B7::TH * B7::XP];
     unsigned h256[256];
     unsigned hx[SEL_L1_BINS];
     unsigned hg[SEL_L1_BINS];
@@ -105,28 +104,21 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
     for (int i = tid; i < SEL_L1_BINS; i += NT) { sm.hx[i] = 0; sm.hg[i] = 0; }
 
     // ---- A: tile + halo ----
-    load_tile<XW, XH, HALO, 0>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) {
-        sm.X[r * XP + c] = (double)v;
-        sm.Q[r * XP + c] = (double)__fmul_rn(v, v);
-    });
+    load_tile<XW, XH, HALO, 0>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) { sm.X[r * XP + c] = v; });
     __syncthreads();
 
     // ---- B: axis-0 box means ----
     const double inv7 = 1.0 / 7.0;
-    {
-        double* const xin[2] = {sm.X, sm.Q};
-        double* const vout[2] = {sm.VS, sm.VQ};
-        box_vertical<7, 2>(xin, vout, inv7);
-    }
+    box_vertical_xq<7>(sm.X, sm.VS, sm.VQ, inv7);
     __syncthreads();
 
     double acc_v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 
     // ---- C: axis-1 box means -> local std ----
     {
-        double* const vin[2] = {sm.VS, sm.VQ};
+        float* const vin[2] = {sm.VS, sm.VQ};
         double ls1 = 0.0, ls2 = 0.0;
-        box_horizontal<7, 2>(vin, inv7, [&](int r, int c, const float (&m)[2]) {
+        box_horizontal_f<7, 2>(vin, inv7, [&](int r, int c, const float (&m)[2]) {
             if (y0 + r < d.h && x0 + c < d.w) {
                 const float lv = fmaxf(__fsub_rn(m[1], __fmul_rn(m[0], m[0])), 0.0f);
                 const double ls = (double)__fsqrt_rn(lv);
@@ -150,22 +142,23 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
         const int cc = c + HALO;
         const int gx = x0 + c;
         const int rbase = wid * 4;
-        const double* col = sm.X + (rbase + HALO - 1) * XP + cc;
+        const float* col = sm.X + (rbase + HALO - 1) * XP + cc;
         double u0 = col[-1], u1 = col[0], u2 = col[1];
         double m0 = col[XP - 1], m1 = col[XP], m2 = col[XP + 1];
+        float xc = col[XP];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = rbase + j;
             const int gy = y0 + r;
-            const double* dn = sm.X + (r + HALO + 1) * XP + cc;
-            const double n0 = dn[-1], n1 = dn[0], n2 = dn[1];
+            const float* dn = sm.X + (r + HALO + 1) * XP + cc;
+            const float xn = dn[0];
+            const double n0 = dn[-1], n1 = xn, n2 = dn[1];
             const bool valid = gy < d.h && gx < d.w;
             // scipy.ndimage.convolve: exact double accumulation, one rounding to float32
             const float lap = (float)(4.0 * m1 - u1 - m0 - m2 - n1);
             const float sh = (float)(0.25 * (u0 - n0) + 0.5 * (u1 - n1) + 0.25 * (u2 - n2));
             const float sv = (float)(0.25 * (u0 - u2) + 0.5 * (m0 - m2) + 0.25 * (n0 - n2));
             const float g = __fsqrt_rn(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
-            const float xc = (float)m1;
             int b256 = (int)(xc * 256.0f);
             b256 = b256 > 255 ? 255 : b256;
             if (valid) {
@@ -185,10 +178,11 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
             }
             // np.histogram(bins=256, range=(0,1)): exact power-of-two edges, out-of-range dropped
             hist_add(sm.h256, b256, valid && xc >= 0.0f && xc <= 1.0f, lane);
-            hist_add(sm.hx, (int)(f2key(xc) >> 21), valid, lane);
-            hist_add(sm.hg, (int)(f2key(g) >> 21), valid, lane);
+            hist_add(sm.hx, (int)(f2key(xc) >> SEL_L1_SHIFT), valid, lane);
+            hist_add(sm.hg, (int)(f2key(g) >> SEL_L1_SHIFT), valid, lane);
             u0 = m0; u1 = m1; u2 = m2;
             m0 = n0; m1 = n1; m2 = n2;
+            xc = xn;
         }
     }
     acc_v[0] = d_x; acc_v[1] = d_x2;
@@ -322,7 +316,7 @@ k_db2_dd(const float* __restrict__ img, Dims d, int hd, int wd, float* __restric
             a = fabsf(a);
             dst[(size_t)oy * wd + ox] = a;
             nz += (a == 0.0f);
-            atomicAdd(&hh[f2key(a) >> 21], 1u);
+            atomicAdd(&hh[f2key(a) >> SEL_L1_SHIFT], 1u);
         }
     }
     __syncthreads();

@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 k_sel_scan(Dims d, int len, int Q, const int* __restrict__ ranks,
            const unsigned* __restrict__ l1_hist, const unsigned* __restrict__ lvl_hist,
            SelState* __restrict__ states, float* __restrict__ out) {
-    constexpr int NB = LEVEL == 3 ? 1024 : 2048;
-    constexpr int SHIFT = LEVEL == 1 ? 21 : (LEVEL == 2 ? 10 : 0);
+    constexpr int NB = LEVEL == 1 ? SEL_L1_BINS : 2048;
+    constexpr int SHIFT = LEVEL == 1 ? SEL_L1_SHIFT : (LEVEL == 2 ? 11 : 0);
     __shared__ unsigned cum[NB];
     __shared__ unsigned warp_tot[SCAN_THREADS / 32];
     __shared__ SelState st;
@@ -109,42 +109,67 @@ k_sel_scan(Dims d, int len, int Q, const int* __restrict__ ranks,
                 out[(size_t)s * Q + q] = (st.valid && st.rank[q] >= 0) ? key2f(st.prefix[q])
                                                                         : __int_as_float(0x7fc00000);
         } else {
-            rebuild_unique(st, Q, LEVEL == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+            rebuild_unique(st, Q, LEVEL == 1 ? 0xFFC00000u : 0xFFFFF800u);
             states[si] = st;
         }
     }
 }
 
 // Histogram the next digit of every element whose resolved prefix matches a query.
+// Almost no element matches: a 2048-bit map of the level-1 bins that hold a query is tested first
+// (one shared-memory word + a shift), only hits walk the prefix list.  128-bit loads when aligned.
 template <int LEVEL>
 __global__ void __launch_bounds__(256)
 k_sel_pass(const float* __restrict__ vals, long long stride, int len, Dims d, int opts,
            const SelState* __restrict__ states, unsigned* __restrict__ lvl_hist) {
-    constexpr unsigned MASK = LEVEL == 2 ? 0xFFE00000u : 0xFFFFFC00u;
+    constexpr unsigned MASK = LEVEL == 2 ? 0xFFC00000u : 0xFFFFF800u;
     __shared__ unsigned up[SEL_MAX_Q];
+    __shared__ unsigned bitmap[SEL_L1_BINS / 32];
     __shared__ int nu_s;
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
+    if (threadIdx.x < SEL_L1_BINS / 32) bitmap[threadIdx.x] = 0;
     if (threadIdx.x == 0) nu_s = states[si].nuniq;
     if (threadIdx.x < SEL_MAX_Q) up[threadIdx.x] = states[si].uprefix[threadIdx.x];
     __syncthreads();
     const int nu = nu_s;
+    if (threadIdx.x < nu) {
+        const unsigned bin = up[threadIdx.x] >> SEL_L1_SHIFT;
+        atomicOr(&bitmap[bin >> 5], 1u << (bin & 31));
+    }
+    __syncthreads();
     const float* v = vals + (size_t)((opts & SEL_COMPACT) ? si : s) * stride;
     const bool use_abs = (opts & SEL_ABS) != 0;
     unsigned* hbase = lvl_hist + (size_t)si * SEL_MAX_Q * 2048;
     const int lane = threadIdx.x & 31;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
-        unsigned key = f2key(use_abs ? fabsf(v[i]) : v[i]);
-        unsigned pre = key & MASK;
-        int u = -1;
-        for (int j = 0; j < nu; ++j) if (up[j] == pre) u = j;
-        if (u >= 0) {
-            unsigned digit = LEVEL == 2 ? ((key >> 10) & 0x7FFu) : (key & 0x3FFu);
-            unsigned slot = (unsigned)u * 2048u + digit;
-            unsigned am = __activemask();
-            unsigned peers = __match_any_sync(am, slot);
-            if (lane == __ffs(peers) - 1) atomicAdd(hbase + slot, (unsigned)__popc(peers));
+
+    auto visit = [&](float f) {
+        const unsigned key = f2key(use_abs ? fabsf(f) : f);
+        const unsigned bin = key >> SEL_L1_SHIFT;
+        if ((bitmap[bin >> 5] >> (bin & 31)) & 1u) {
+            const unsigned pre = key & MASK;
+            int u = -1;
+            for (int j = 0; j < nu; ++j) if (up[j] == pre) u = j;
+            if (u >= 0) {
+                const unsigned digit = LEVEL == 2 ? ((key >> 11) & 0x7FFu) : (key & 0x7FFu);
+                const unsigned slot = (unsigned)u * 2048u + digit;
+                const unsigned am = __activemask();
+                const unsigned peers = __match_any_sync(am, slot);
+                if (lane == __ffs(peers) - 1) atomicAdd(hbase + slot, (unsigned)__popc(peers));
+            }
         }
+    };
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if ((((uintptr_t)v) & 15) == 0) {
+        const int n4 = len >> 2;
+        const float4* v4 = reinterpret_cast<const float4*>(v);
+        for (int i = tid; i < n4; i += nthr) {
+            const float4 q = v4[i];
+            visit(q.x); visit(q.y); visit(q.z); visit(q.w);
+        }
+        for (int i = (n4 << 2) + tid; i < len; i += nthr) visit(v[i]);
+    } else {
+        for (int i = tid; i < len; i += nthr) visit(v[i]);
     }
 }
 

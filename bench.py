@@ -285,7 +285,7 @@ def run_gpu(args) -> None:
     value = px_per_step * args.steps / (ms_total / 1e3) / 1e6
     e2e_value = px_per_step * e2e_steps / (ms_e2e / 1e3) / 1e6
 
-    # ---- roofline of the dominant kernel (k_tv_iter: 20 B/px per launch) ----
+    # ---- roofline of the dominant kernel (TV-Chambolle body: 20 B/px algorithmic) ----
     roof = None
     cpu_base = None
     if rank == 0:
@@ -308,21 +308,22 @@ def run_gpu(args) -> None:
         achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9
         tv_iters = last.tv_iterations
         traffic = None
-        tj = ROOT / "profiles" / "r01_tv_pair_traffic.json"
+        tj = ROOT / "profiles" / "r01_tvp_traffic.json"
         if tj.exists():
             try:
                 traffic = float(json.loads(tj.read_text())["dram_bytes_per_pixel_per_body"]) * chunk * H * W
             except Exception:  # noqa: BLE001
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "k_tv_pair", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "k_tvp<2> (TV-Chambolle, packed two-pixel kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per pixel and body "
-                                  "(profiles/r01_tv_pair_traffic.json) x pixels of this launch",
+                                  "(profiles/r01_tvp_traffic.json) x pixels of this launch",
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "launch_ms": per_launch_ms,
                 "note": f"per loop body: 20 B/px (x 4 + p 8 read, p 8 written) x {chunk} slices x 512x512; one "
-                        f"k_tv_pair launch runs two bodies and keeps the intermediate p in registers, so its "
-                        f"DRAM traffic is about half the algorithmic figure; timed as (41 - 1 bodies) / 40 with "
+                        f"k_tvp launch runs two bodies and keeps the intermediate p in registers, so its "
+                        f"DRAM traffic is about half the algorithmic figure (achieved can exceed the HBM peak); "
+                        f"measured limiter: FP32 pipe + issue, DRAM at 53 %; timed as (41 - 1 bodies) / 40 with "
                         f"CUDA events; mean TV iterations/slice in the workload = {float(tv_iters.mean()):.1f}"}
         if not args.no_cpu:
             cores = len(os.sched_getaffinity(0))

@@ -235,6 +235,43 @@ def test_tv_in_place_and_iteration_cap(ops, dev, images):
     np.testing.assert_array_equal(host(x), ref)
 
 
+@pytest.mark.parametrize("knobs", [{"MDIMG_TV_K": "4"}, {"MDIMG_TV_MINB": "3"}, {"MDIMG_TV_PACKED": "0"},
+                                   {"MDIMG_TV_K": "4", "MDIMG_TV_MINB": "3"}])
+@pytest.mark.parametrize("cap", [1, 2, 3, 4, 5, 6, 7, 9, 200])
+def test_tv_kernel_variants_and_replay(ops, dev, monkeypatch, knobs, cap):
+    """Every launch schedule (2 / 4 bodies per launch, tail launches, replay of 1-3 bodies when the
+    loop stops inside a launch) and both kernel families give the oracle's field bit for bit."""
+    rng = np.random.default_rng(77)
+    im = rng.random((150, 136), dtype=np.float32)
+    im[:40] = 0.0                       # exactly flat region: tiny operands at its diffusion front
+    im[:, 100:] *= 1e-3
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    x = dev(im)
+    out = torch.empty_like(x)
+    eps = 2.0e-4 if cap == 200 else 0.0
+    iters = int(ops.tv_chambolle(x, out, 0.08, eps=eps, max_iter=cap)[0].item())
+    ref, ref_iters = ores.denoise_tv_chambolle(im, 0.08, eps=eps, max_num_iter=cap, return_iters=True)
+    assert abs(iters - ref_iters) <= 1
+    if iters == ref_iters:
+        np.testing.assert_array_equal(host(out), ref)
+
+
+def test_tv_stack_slices_stop_independently(ops):
+    """A stack whose slices need different iteration counts: every slice equals its own single-slice run."""
+    rng = np.random.default_rng(5)
+    ims = [rng.random((96, 128), dtype=np.float32) * s for s in (1.0, 0.2, 0.02)]
+    ims.append(np.zeros((96, 128), np.float32))
+    xs = torch.from_numpy(np.stack(ims)).to(ops.device)
+    out = torch.empty_like(xs)
+    its = ops.tv_chambolle(xs, out, 0.1).cpu().numpy()
+    for z, im in enumerate(ims):
+        ref, ref_iters = ores.denoise_tv_chambolle(im, 0.1, return_iters=True)
+        assert abs(int(its[z]) - ref_iters) <= 1
+        if int(its[z]) == ref_iters:
+            np.testing.assert_array_equal(out[z].cpu().numpy(), ref)
+
+
 # ------------------------------------------------------------------ stack semantics
 def test_stack_rows_equal_per_slice_rows_and_sel_is_respected(ops, synth):
     stack = np.stack([omet.normalize_image(synth.ct_slice(1000 + z, z / 8)) for z in range(8)])

@@ -178,8 +178,8 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
             }
             // np.histogram(bins=256, range=(0,1)): exact power-of-two edges, out-of-range dropped
             hist_add(sm.h256, b256, valid && xc >= 0.0f && xc <= 1.0f, lane);
-            hist_add(sm.hx, (int)(f2key(xc) >> SEL_L1_SHIFT), valid, lane);
-            hist_add(sm.hg, (int)(f2key(g) >> SEL_L1_SHIFT), valid, lane);
+            hist_add(sm.hx, sel_bin1(xc), valid, lane);
+            hist_add(sm.hg, sel_bin1(g), valid, lane);
             u0 = m0; u1 = m1; u2 = m2;
             m0 = n0; m1 = n1; m2 = n2;
             xc = xn;
@@ -316,7 +316,7 @@ k_db2_dd(const float* __restrict__ img, Dims d, int hd, int wd, float* __restric
             a = fabsf(a);
             dst[(size_t)oy * wd + ox] = a;
             nz += (a == 0.0f);
-            atomicAdd(&hh[f2key(a) >> SEL_L1_SHIFT], 1u);
+            atomicAdd(&hh[sel_bin1(a)], 1u);
         }
     }
     __syncthreads();
@@ -558,15 +558,28 @@ void carve_sigma(Arena& a, int n, int n_sel, int hd, int wd, SigmaBufs& b) {
     b.sel_ws = a.take<char>(b.sel_ws_bytes);
 }
 
-int sigma_core(const float* img, const Dims& d, MetAcc* acc, SigmaBufs& b, double* sigma_out,
-               cudaStream_t stream) {
+// db2 'dd' band + level-1 histogram + median ranks (everything before the selection)
+void sigma_produce(const float* img, const Dims& d, MetAcc* acc, SigmaBufs& b, cudaStream_t stream) {
     const int hd = (d.h + 3) / 2, wd = (d.w + 3) / 2;
     cudaMemsetAsync(b.l1, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
     dim3 grid(((wd + DT - 1) / DT) * ((hd + DT - 1) / DT), d.n_sel);
     MDIMG_LAUNCH k_db2_dd<<<grid, NT, 0, stream>>>(img, d, hd, wd, b.absdd, b.l1, acc);
     MDIMG_LAUNCH k_sigma_ranks<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, hd * wd, acc, b.ranks);
-    int rc = select_run(b.absdd, (long long)hd * wd, hd * wd, d, 2, b.ranks, b.l1, b.sel_out,
-                        b.sel_ws, b.sel_ws_bytes, stream);
+}
+
+SelJob sigma_job(const Dims& d, const SigmaBufs& b) {
+    const int hd = (d.h + 3) / 2, wd = (d.w + 3) / 2;
+    SelJob j;
+    j.vals = b.absdd; j.stride = (long long)hd * wd; j.len = hd * wd; j.Q = 2; j.opts = 0;
+    j.ranks = b.ranks; j.l1_hist = b.l1; j.out = b.sel_out; j.ws = b.sel_ws;
+    return j;
+}
+
+int sigma_core(const float* img, const Dims& d, MetAcc* acc, SigmaBufs& b, double* sigma_out,
+               cudaStream_t stream) {
+    sigma_produce(img, d, acc, b, stream);
+    const SelJob j = sigma_job(d, b);
+    int rc = select_run_multi(&j, 1, d, stream);
     if (rc) return rc;
     MDIMG_LAUNCH k_sigma_out<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, b.sel_out, sigma_out);
     return check_launch("estimate_sigma");
@@ -626,7 +639,7 @@ namespace {
 struct MetBufs {
     MetAcc* acc; float* g; unsigned* l1x; unsigned* l1g; int* plan_ranks; int* xranks; int* granks;
     float* xsel; float* gsel; GradPrep* prep; double* sigma; double* box2;
-    void* sel_ws; size_t sel_ws_bytes; SigmaBufs sb;
+    void* sel_ws; void* sel_ws_g; size_t sel_ws_bytes; SigmaBufs sb;
 };
 void carve_metrics(Arena& a, int n, int n_sel, int h, int w, MetBufs& m) {
     m.acc = a.take<MetAcc>(n_sel);
@@ -643,6 +656,7 @@ void carve_metrics(Arena& a, int n, int n_sel, int h, int w, MetBufs& m) {
     m.box2 = a.take<double>((size_t)n_sel * 2);
     m.sel_ws_bytes = select_workspace_bytes(n_sel);
     m.sel_ws = a.take<char>(m.sel_ws_bytes);
+    m.sel_ws_g = a.take<char>(m.sel_ws_bytes);
     carve_sigma(a, n, n_sel, (h + 3) / 2, (w + 3) / 2, m.sb);
 }
 }  // namespace
@@ -678,21 +692,26 @@ int metrics_run(const float* img, const Dims& d, const PctPlan& plan, int flags,
     int rc = check_launch("stencil_stats");
     if (rc) return rc;
 
-    // sigma (db2 'dd' median)
-    rc = sigma_core(img, d, m.acc, m.sb, m.sigma, stream);
-    if (rc) return rc;
+    // db2 'dd' band of estimate_sigma (+ its level-1 histogram and median ranks)
+    sigma_produce(img, d, m.acc, m.sb, stream);
 
-    // percentiles of x: ranks (lo,hi) for 5, 25, 75, 95; of |grad|: 90
+    // percentiles of x: ranks (lo,hi) for 5, 25, 75, 95; of |grad|: 90; median of |dd|:
+    // three selections refined by the same launches
     int host_ranks[10];
     for (int k = 0; k < 4; ++k) { host_ranks[2 * k] = plan.lo[k]; host_ranks[2 * k + 1] = plan.hi[k]; }
     host_ranks[8] = plan.lo[4]; host_ranks[9] = plan.hi[4];
     cudaMemcpyAsync(m.plan_ranks, host_ranks, sizeof(host_ranks), cudaMemcpyHostToDevice, stream);
     MDIMG_LAUNCH k_fill_ranks<<<(d.n_sel * 8 + 127) / 128, 128, 0, stream>>>(d, 8, m.plan_ranks, m.xranks);
     MDIMG_LAUNCH k_fill_ranks<<<(d.n_sel * 2 + 127) / 128, 128, 0, stream>>>(d, 2, m.plan_ranks + 8, m.granks);
-    rc = select_run(img, (long long)len, len, d, 8, m.xranks, m.l1x, m.xsel, m.sel_ws, m.sel_ws_bytes, stream);
+    SelJob jobs[3];
+    jobs[0].vals = img; jobs[0].stride = len; jobs[0].len = len; jobs[0].Q = 8; jobs[0].opts = 0;
+    jobs[0].ranks = m.xranks; jobs[0].l1_hist = m.l1x; jobs[0].out = m.xsel; jobs[0].ws = m.sel_ws;
+    jobs[1].vals = m.g; jobs[1].stride = len; jobs[1].len = len; jobs[1].Q = 2; jobs[1].opts = 0;
+    jobs[1].ranks = m.granks; jobs[1].l1_hist = m.l1g; jobs[1].out = m.gsel; jobs[1].ws = m.sel_ws_g;
+    jobs[2] = sigma_job(d, m.sb);
+    rc = select_run_multi(jobs, 3, d, stream);
     if (rc) return rc;
-    rc = select_run(m.g, (long long)len, len, d, 2, m.granks, m.l1g, m.gsel, m.sel_ws, m.sel_ws_bytes, stream);
-    if (rc) return rc;
+    MDIMG_LAUNCH k_sigma_out<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, m.sb.sel_out, m.sigma);
 
     MDIMG_LAUNCH k_grad_prep<<<d.n_sel, 160, 0, stream>>>(d, m.acc, m.gsel, plan.gamma[4], m.prep);
     int bx = (len + NT * 8 - 1) / (NT * 8);

@@ -1,22 +1,39 @@
-// Exact multi-query radix select (see select.cuh).
+// Exact multi-query range select (see select.cuh).
 #include "select.cuh"
 
 namespace mdimg {
 
 namespace {
 
-constexpr int SCAN_THREADS = 256;
+constexpr int ST = 256;                       // threads per block (scan and refine)
+constexpr unsigned KEY_NEG_INF = 0x007FFFFFu; // f2key(-inf)
+constexpr unsigned KEY_POS_INF = 0xFF800000u; // f2key(+inf)
 
-// Inclusive scan of `nb` bins (nb = 256 * K) into smem `cum`; every thread of the block calls.
-template <int K>
-__device__ void block_inclusive_scan(const unsigned* __restrict__ hist, unsigned* cum,
-                                     unsigned* warp_tot) {
+struct JobDev {
+    const float* vals;
+    long long stride;
+    int len, Q, opts;
+    const int* ranks;
+    const unsigned* l1;
+    float* out;
+    SelState* states;
+    unsigned* hist;        // [n_sel][SEL_MAX_Q][SEL_REFINE_BINS], zero between passes
+    unsigned* counters;    // [n_sel] block tickets, zero between passes
+};
+
+struct Params {
+    JobDev job[SEL_MAX_JOBS];
+};
+
+// Inclusive scan of 256 * K bins into smem `cum`; every thread of the block calls.
+template <int K, typename Load>
+__device__ void block_inclusive_scan(Load&& load, unsigned* cum, unsigned* warp_tot) {
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     unsigned loc[K];
     unsigned run = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        run += hist[t * K + k];
+        run += load(t * K + k);
         loc[k] = run;
     }
     unsigned inc = run;
@@ -25,6 +42,7 @@ __device__ void block_inclusive_scan(const unsigned* __restrict__ hist, unsigned
         unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += v;
     }
+    __syncthreads();                 // previous users of cum / warp_tot are done
     if (lane == 31) warp_tot[wid] = inc;
     __syncthreads();
     unsigned base = 0;
@@ -45,121 +63,140 @@ __device__ int upper_bin(const unsigned* cum, int nb, unsigned rank) {
     return lo;
 }
 
-__device__ void rebuild_unique(SelState& st, int Q, unsigned mask) {
+// smallest key in [f2key(-inf), f2key(+inf) + 1] whose level-1 bin is >= b
+__device__ unsigned first_key_of_bin(int b) {
+    unsigned lo = KEY_NEG_INF, hi = KEY_POS_INF + 1u;
+    while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        if (sel_bin1(key2f(mid)) >= b) hi = mid; else lo = mid + 1u;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int shift_for(unsigned span) {
+    const int bits = 32 - __clz(span);            // span >= 1
+    return bits > 11 ? bits - 11 : 0;
+}
+
+__device__ __forceinline__ float nan_f() { return __int_as_float(0x7fc00000); }
+
+// Group the unresolved queries by key range (thread 0 only).
+__device__ void rebuild_unique(SelState& st, int Q) {
     int nu = 0;
     for (int q = 0; q < Q; ++q) {
-        unsigned p = st.prefix[q] & mask;
+        if (st.uid[q] < 0) continue;
         int u = -1;
-        for (int j = 0; j < nu; ++j) if (st.uprefix[j] == p) { u = j; break; }
-        if (u < 0) { u = nu; st.uprefix[nu++] = p; }
+        for (int j = 0; j < nu; ++j)
+            if (st.ulo[j] == st.lo[q] && st.uspan[j] == st.span[q]) { u = j; break; }
+        if (u < 0) {
+            u = nu++;
+            st.ulo[u] = st.lo[q];
+            st.uspan[u] = st.span[q];
+            st.ushift[u] = shift_for(st.span[q]);
+            st.ubin[u] = sel_bin1(key2f(st.lo[q]));
+        }
         st.uid[q] = u;
     }
     st.nuniq = nu;
 }
 
-// LEVEL 1: hist = l1_hist[slice]; LEVEL 2/3: hist = lvl_hist[si][uid][...].
-template <int LEVEL>
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_sel_scan(Dims d, int len, int Q, const int* __restrict__ ranks,
-           const unsigned* __restrict__ l1_hist, const unsigned* __restrict__ lvl_hist,
-           SelState* __restrict__ states, float* __restrict__ out) {
-    constexpr int NB = LEVEL == 1 ? SEL_L1_BINS : 2048;
-    constexpr int SHIFT = LEVEL == 1 ? SEL_L1_SHIFT : (LEVEL == 2 ? 11 : 0);
-    __shared__ unsigned cum[NB];
-    __shared__ unsigned warp_tot[SCAN_THREADS / 32];
+// Level 1: locate every query's bin in the producer's histogram.
+__global__ void __launch_bounds__(ST)
+k_sel_scan1(Params P, Dims d) {
+    __shared__ unsigned cum[SEL_L1_BINS];
+    __shared__ unsigned warp_tot[ST / 32];
     __shared__ SelState st;
+    const JobDev& J = P.job[blockIdx.y];
     const int si = blockIdx.x;
     const int s = slice_of(d.sel, si);
-    if (threadIdx.x == 0) {
-        if (LEVEL == 1) {
-            st.valid = len > 0;
-            for (int q = 0; q < Q; ++q) {
-                st.prefix[q] = 0;
-                st.rank[q] = ranks[(size_t)s * Q + q];
-                st.uid[q] = 0;
-            }
-            st.nuniq = 1;
-            st.uprefix[0] = 0;
+    const unsigned* h = J.l1 + (size_t)si * SEL_L1_BINS;
+    block_inclusive_scan<SEL_L1_BINS / ST>([&](int i) { return h[i]; }, cum, warp_tot);
+    const int q = threadIdx.x;
+    if (q < SEL_MAX_Q) {
+        st.uid[q] = -1;
+        st.rank[q] = -1;
+        st.lo[q] = 0;
+        st.span[q] = 0;
+    }
+    if (q < J.Q) {
+        const int r = J.ranks[(size_t)s * J.Q + q];
+        if (J.len <= 0 || r < 0 || (unsigned)r >= cum[SEL_L1_BINS - 1]) {
+            J.out[(size_t)s * J.Q + q] = nan_f();
         } else {
-            st = states[si];
+            const int b = upper_bin(cum, SEL_L1_BINS, (unsigned)r);
+            const unsigned below = b ? cum[b - 1] : 0u;
+            unsigned lo, hi;
+            if (b == 1) {
+                lo = hi = 0x80000000u;                 // exact zero (sel_key folds -0.0 into +0.0)
+            } else {
+                lo = first_key_of_bin(b);
+                hi = first_key_of_bin(b + 1) - 1u;
+            }
+            st.rank[q] = r - (int)below;
+            st.lo[q] = lo;
+            st.span[q] = hi - lo;
+            if (hi == lo) J.out[(size_t)s * J.Q + q] = key2f(lo);
+            else st.uid[q] = 0;
         }
     }
     __syncthreads();
-    const int nu = st.nuniq;
-    for (int u = 0; u < nu; ++u) {
-        const unsigned* h = LEVEL == 1 ? l1_hist + (size_t)si * SEL_L1_BINS
-                                       : lvl_hist + ((size_t)si * SEL_MAX_Q + u) * 2048;
-        block_inclusive_scan<NB / SCAN_THREADS>(h, cum, warp_tot);
-        if (threadIdx.x == 0) {
-            for (int q = 0; q < Q; ++q) {
-                if (st.uid[q] != u) continue;
-                int r = st.rank[q];
-                if (r < 0 || (unsigned)r >= cum[NB - 1]) { st.rank[q] = -1; continue; }
-                int b = upper_bin(cum, NB, (unsigned)r);
-                unsigned below = b ? cum[b - 1] : 0u;
-                st.prefix[q] |= (unsigned)b << SHIFT;
-                st.rank[q] = r - (int)below;
-            }
-        }
-        __syncthreads();
-    }
     if (threadIdx.x == 0) {
-        if (LEVEL == 3) {
-            for (int q = 0; q < Q; ++q)
-                out[(size_t)s * Q + q] = (st.valid && st.rank[q] >= 0) ? key2f(st.prefix[q])
-                                                                        : __int_as_float(0x7fc00000);
-        } else {
-            rebuild_unique(st, Q, LEVEL == 1 ? 0xFFC00000u : 0xFFFFF800u);
-            states[si] = st;
-        }
+        st.valid = J.len > 0;
+        rebuild_unique(st, J.Q);
+        J.states[si] = st;
     }
 }
 
-// Histogram the next digit of every element whose resolved prefix matches a query.
-// Almost no element matches: a 2048-bit map of the level-1 bins that hold a query is tested first
-// (one shared-memory word + a shift), only hits walk the prefix list.  128-bit loads when aligned.
-template <int LEVEL>
-__global__ void __launch_bounds__(256)
-k_sel_pass(const float* __restrict__ vals, long long stride, int len, Dims d, int opts,
-           const SelState* __restrict__ states, unsigned* __restrict__ lvl_hist) {
-    constexpr unsigned MASK = LEVEL == 2 ? 0xFFC00000u : 0xFFFFF800u;
-    __shared__ unsigned up[SEL_MAX_Q];
+// One refinement pass (+ the slice's scan, done by the last block to finish).
+__global__ void __launch_bounds__(ST)
+k_sel_refine(Params P, Dims d) {
+    __shared__ unsigned ulo[SEL_MAX_Q], uspan[SEL_MAX_Q];
+    __shared__ int ushift[SEL_MAX_Q];
     __shared__ unsigned bitmap[SEL_L1_BINS / 32];
-    __shared__ int nu_s;
+    __shared__ int nu_s, last_s;
+    __shared__ unsigned cum[SEL_REFINE_BINS];
+    __shared__ unsigned warp_tot[ST / 32];
+    __shared__ SelState st;
+    const JobDev& J = P.job[blockIdx.z];
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
+    const SelState* gst = J.states + si;
     if (threadIdx.x < SEL_L1_BINS / 32) bitmap[threadIdx.x] = 0;
-    if (threadIdx.x == 0) nu_s = states[si].nuniq;
-    if (threadIdx.x < SEL_MAX_Q) up[threadIdx.x] = states[si].uprefix[threadIdx.x];
+    if (threadIdx.x == 0) nu_s = gst->nuniq;
     __syncthreads();
     const int nu = nu_s;
+    if (nu == 0) return;                           // every query of this slice is resolved
     if (threadIdx.x < nu) {
-        const unsigned bin = up[threadIdx.x] >> SEL_L1_SHIFT;
+        ulo[threadIdx.x] = gst->ulo[threadIdx.x];
+        uspan[threadIdx.x] = gst->uspan[threadIdx.x];
+        ushift[threadIdx.x] = gst->ushift[threadIdx.x];
+        const int bin = gst->ubin[threadIdx.x];
         atomicOr(&bitmap[bin >> 5], 1u << (bin & 31));
     }
     __syncthreads();
-    const float* v = vals + (size_t)((opts & SEL_COMPACT) ? si : s) * stride;
-    const bool use_abs = (opts & SEL_ABS) != 0;
-    unsigned* hbase = lvl_hist + (size_t)si * SEL_MAX_Q * 2048;
+    const float* v = J.vals + (size_t)((J.opts & SEL_COMPACT) ? si : s) * J.stride;
+    const bool use_abs = (J.opts & SEL_ABS) != 0;
+    unsigned* hbase = J.hist + (size_t)si * SEL_MAX_Q * SEL_REFINE_BINS;
     const int lane = threadIdx.x & 31;
+    const int len = J.len;
 
     auto visit = [&](float f) {
-        const unsigned key = f2key(use_abs ? fabsf(f) : f);
-        const unsigned bin = key >> SEL_L1_SHIFT;
+        f = __fadd_rn(use_abs ? fabsf(f) : f, 0.0f);
+        const int bin = sel_bin1(f);
         if ((bitmap[bin >> 5] >> (bin & 31)) & 1u) {
-            const unsigned pre = key & MASK;
-            int u = -1;
-            for (int j = 0; j < nu; ++j) if (up[j] == pre) u = j;
-            if (u >= 0) {
-                const unsigned digit = LEVEL == 2 ? ((key >> 11) & 0x7FFu) : (key & 0x7FFu);
-                const unsigned slot = (unsigned)u * 2048u + digit;
-                const unsigned am = __activemask();
-                const unsigned peers = __match_any_sync(am, slot);
-                if (lane == __ffs(peers) - 1) atomicAdd(hbase + slot, (unsigned)__popc(peers));
+            const unsigned key = f2key(f);
+            for (int j = 0; j < nu; ++j) {
+                const unsigned off = key - ulo[j];
+                if (off <= uspan[j]) {
+                    const unsigned slot = (unsigned)j * SEL_REFINE_BINS + (off >> ushift[j]);
+                    const unsigned peers = __match_any_sync(__activemask(), slot);
+                    if (lane == __ffs(peers) - 1) atomicAdd(hbase + slot, (unsigned)__popc(peers));
+                    break;
+                }
             }
         }
     };
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const int tid = blockIdx.x * ST + threadIdx.x, nthr = gridDim.x * ST;
     if ((((uintptr_t)v) & 15) == 0) {
         const int n4 = len >> 2;
         const float4* v4 = reinterpret_cast<const float4*>(v);
@@ -171,41 +208,109 @@ k_sel_pass(const float* __restrict__ vals, long long stride, int len, Dims d, in
     } else {
         for (int i = tid; i < len; i += nthr) visit(v[i]);
     }
+
+    // ---- last block of this slice: scan the digit histograms, narrow the ranges ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_s = (atomicAdd(J.counters + si, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    if (threadIdx.x == 0) st = *gst;
+    __syncthreads();
+    for (int u = 0; u < nu; ++u) {
+        unsigned* row = hbase + (size_t)u * SEL_REFINE_BINS;
+        block_inclusive_scan<SEL_REFINE_BINS / ST>([&](int i) { return __ldcg(row + i); }, cum, warp_tot);
+        const int q = threadIdx.x;
+        if (q < J.Q && st.uid[q] == u) {
+            const int r = st.rank[q];
+            if (r < 0 || (unsigned)r >= cum[SEL_REFINE_BINS - 1]) {     // cannot happen for consistent histograms
+                st.rank[q] = -1;
+                st.uid[q] = -1;
+                J.out[(size_t)s * J.Q + q] = nan_f();
+            } else {
+                const int b = upper_bin(cum, SEL_REFINE_BINS, (unsigned)r);
+                const unsigned below = b ? cum[b - 1] : 0u;
+                const int sh = st.ushift[u];
+                const unsigned base = (unsigned)b << sh;
+                const unsigned width = sh ? ((1u << sh) - 1u) : 0u;
+                st.rank[q] = r - (int)below;
+                st.lo[q] = st.ulo[u] + base;
+                st.span[q] = min(st.uspan[u] - base, width);
+                if (st.span[q] == 0) {
+                    st.uid[q] = -1;
+                    J.out[(size_t)s * J.Q + q] = key2f(st.lo[q]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEL_REFINE_BINS; i += ST) row[i] = 0;   // ready for the next pass
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rebuild_unique(st, J.Q);
+        J.states[si] = st;
+        J.counters[si] = 0;
+    }
+}
+
+struct Carve { SelState* states; unsigned* hist; unsigned* counters; size_t zero_off, zero_bytes; };
+
+void carve(Arena& a, int n_sel, Carve& c) {
+    c.states = a.take<SelState>(n_sel);
+    c.zero_off = a.off;
+    c.hist = a.take<unsigned>((size_t)n_sel * SEL_MAX_Q * SEL_REFINE_BINS);
+    c.counters = a.take<unsigned>(n_sel);
+    c.zero_bytes = a.off - c.zero_off;
 }
 
 }  // namespace
 
 size_t select_workspace_bytes(int n_sel) {
     Arena a(nullptr, 0);
-    a.take<SelState>(n_sel);
-    a.take<unsigned>((size_t)n_sel * SEL_MAX_Q * 2048);
+    Carve c;
+    carve(a, n_sel, c);
     return a.off;
+}
+
+int select_run_multi(const SelJob* jobs, int njobs, const Dims& d, cudaStream_t stream) {
+    if (njobs < 1 || njobs > SEL_MAX_JOBS) return set_error(MDIMG_ERR_INVALID, "select: %d jobs", njobs);
+    if (d.n_sel == 0) return MDIMG_OK;
+    Params P;
+    int max_len = 1;
+    const size_t need = select_workspace_bytes(d.n_sel);
+    for (int j = 0; j < njobs; ++j) {
+        const SelJob& in = jobs[j];
+        if (in.Q < 1 || in.Q > SEL_MAX_Q) return set_error(MDIMG_ERR_INVALID, "select: Q=%d out of range", in.Q);
+        Arena a(in.ws, need);
+        Carve c;
+        carve(a, d.n_sel, c);
+        JobDev& o = P.job[j];
+        o.vals = in.vals; o.stride = in.stride; o.len = in.len; o.Q = in.Q; o.opts = in.opts;
+        o.ranks = in.ranks; o.l1 = in.l1_hist; o.out = in.out;
+        o.states = c.states; o.hist = c.hist; o.counters = c.counters;
+        cudaMemsetAsync((char*)in.ws + c.zero_off, 0, c.zero_bytes, stream);
+        if (in.len > max_len) max_len = in.len;
+    }
+    for (int j = njobs; j < SEL_MAX_JOBS; ++j) P.job[j] = P.job[0];
+    int bx = (max_len + ST * 16 - 1) / (ST * 16);
+    if (bx < 1) bx = 1;
+    if (bx > 1024) bx = 1024;
+    MDIMG_LAUNCH k_sel_scan1<<<dim3(d.n_sel, njobs), ST, 0, stream>>>(P, d);
+    // key ranges of a level-1 bin span at most 2^31 keys: three 11-bit refinements always resolve
+    for (int level = 0; level < 3; ++level)
+        MDIMG_LAUNCH k_sel_refine<<<dim3(bx, d.n_sel, njobs), ST, 0, stream>>>(P, d);
+    return check_launch("select");
 }
 
 int select_run(const float* vals, long long stride, int len, const Dims& d, int Q,
                const int* ranks, const unsigned* l1_hist, float* out,
                void* ws, size_t ws_bytes, cudaStream_t stream, int opts) {
-    if (Q < 1 || Q > SEL_MAX_Q) return set_error(MDIMG_ERR_INVALID, "select: Q=%d out of range", Q);
-    Arena a(ws, ws_bytes);
-    SelState* states = a.take<SelState>(d.n_sel);
-    size_t hist_elems = (size_t)d.n_sel * SEL_MAX_Q * 2048;
-    unsigned* hist = a.take<unsigned>(hist_elems);
-    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "select: workspace too small");
-    if (d.n_sel == 0) return MDIMG_OK;
-
-    int bx = (len + 256 * 8 - 1) / (256 * 8);
-    if (bx < 1) bx = 1;
-    if (bx > 1024) bx = 1024;
-    dim3 pgrid(bx, d.n_sel);
-
-    MDIMG_LAUNCH k_sel_scan<1><<<d.n_sel, SCAN_THREADS, 0, stream>>>(d, len, Q, ranks, l1_hist, nullptr, states, out);
-    cudaMemsetAsync(hist, 0, hist_elems * sizeof(unsigned), stream);
-    MDIMG_LAUNCH k_sel_pass<2><<<pgrid, 256, 0, stream>>>(vals, stride, len, d, opts, states, hist);
-    MDIMG_LAUNCH k_sel_scan<2><<<d.n_sel, SCAN_THREADS, 0, stream>>>(d, len, Q, ranks, l1_hist, hist, states, out);
-    cudaMemsetAsync(hist, 0, hist_elems * sizeof(unsigned), stream);
-    MDIMG_LAUNCH k_sel_pass<3><<<pgrid, 256, 0, stream>>>(vals, stride, len, d, opts, states, hist);
-    MDIMG_LAUNCH k_sel_scan<3><<<d.n_sel, SCAN_THREADS, 0, stream>>>(d, len, Q, ranks, l1_hist, hist, states, out);
-    return check_launch("select");
+    if (ws_bytes < select_workspace_bytes(d.n_sel)) return set_error(MDIMG_ERR_WORKSPACE, "select: workspace too small");
+    SelJob j;
+    j.vals = vals; j.stride = stride; j.len = len; j.Q = Q; j.opts = opts;
+    j.ranks = ranks; j.l1_hist = l1_hist; j.out = out; j.ws = ws;
+    return select_run_multi(&j, 1, d, stream);
 }
 
 }  // namespace mdimg

@@ -115,7 +115,7 @@ k_haar_fwd(const float* __restrict__ in, long long in_stride, int h0, int w0, Di
         if (hist) {
             const float a = fabsf(dd);
             nz += (a == 0.0f);
-            atomicAdd(&hh[f2key(a) >> SEL_L1_SHIFT], 1u);
+            atomicAdd(&hh[sel_bin1(a)], 1u);
         }
     }
     WaveAcc* A = acc + si;

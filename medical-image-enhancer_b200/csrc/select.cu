@@ -200,11 +200,19 @@ k_sel_refine(Params P, Dims d) {
     if ((((uintptr_t)v) & 15) == 0) {
         const int n4 = len >> 2;
         const float4* v4 = reinterpret_cast<const float4*>(v);
-        for (int i = tid; i < n4; i += nthr) {
+        int i = tid;
+        for (; i + 3 * nthr < n4; i += 4 * nthr) {                 // four independent 128-bit loads in flight
+            const float4 a = v4[i], b = v4[i + nthr], c = v4[i + 2 * nthr], e = v4[i + 3 * nthr];
+            visit(a.x); visit(a.y); visit(a.z); visit(a.w);
+            visit(b.x); visit(b.y); visit(b.z); visit(b.w);
+            visit(c.x); visit(c.y); visit(c.z); visit(c.w);
+            visit(e.x); visit(e.y); visit(e.z); visit(e.w);
+        }
+        for (; i < n4; i += nthr) {
             const float4 q = v4[i];
             visit(q.x); visit(q.y); visit(q.z); visit(q.w);
         }
-        for (int i = (n4 << 2) + tid; i < len; i += nthr) visit(v[i]);
+        for (int k = (n4 << 2) + tid; k < len; k += nthr) visit(v[k]);
     } else {
         for (int i = tid; i < len; i += nthr) visit(v[i]);
     }
@@ -293,9 +301,11 @@ int select_run_multi(const SelJob* jobs, int njobs, const Dims& d, cudaStream_t 
         if (in.len > max_len) max_len = in.len;
     }
     for (int j = njobs; j < SEL_MAX_JOBS; ++j) P.job[j] = P.job[0];
-    int bx = (max_len + ST * 16 - 1) / (ST * 16);
+    // few, long-lived blocks per slice: the per-block cost (state load, fence, ticket) is a few
+    // microseconds of dependent latency
+    int bx = (max_len + ST * 64 - 1) / (ST * 64);
     if (bx < 1) bx = 1;
-    if (bx > 1024) bx = 1024;
+    if (bx > 256) bx = 256;
     MDIMG_LAUNCH k_sel_scan1<<<dim3(d.n_sel, njobs), ST, 0, stream>>>(P, d);
     // key ranges of a level-1 bin span at most 2^31 keys: three 11-bit refinements always resolve
     for (int level = 0; level < 3; ++level)

@@ -136,27 +136,43 @@ k_haar_fwd(const float* __restrict__ in, long long in_stride, int h0, int w0, Di
 // move a pixel across a CLAHE bin edge downstream, so the order is reproduced exactly: a leaf
 // table and a post-order combine program are built on the host for each band length.
 struct PwLeaf { int level; int off; int len; };          // off: element offset inside the band
-struct PwLevel { int leaf0; int n_leaf; int prog0; int n_prog; long long det_off; long long band; };
+// An internal node adds the sum of its right subtree (first leaf m) to that of its left subtree
+// (first leaf a); a node's value lives in the slot of its first leaf, so the combine is in place.
+struct PwNode { int a; int m; };
+constexpr int PW_MAX_ROUNDS = 40;
+struct PwLevel {
+    int leaf0; int n_leaf;
+    int node0;                              // first node of this level in the node table (sorted by height)
+    int n_rounds;                           // tree height
+    int round_end[PW_MAX_ROUNDS];           // nodes of height <= r + 1 end here (relative to node0)
+    long long det_off; long long band;
+};
 
 struct PwPlan {
     std::vector<PwLeaf> leaves;
-    std::vector<unsigned char> prog;       // 0 = push next leaf sum, 1 = pop two, push their sum
+    std::vector<PwNode> nodes;
     std::vector<PwLevel> levels;           // index 0 unused
     int max_depth = 0;
 };
 
-void pw_build(int off, int n, int level, PwPlan& p, int depth) {
+struct PwTmpNode { int a, m, height; };
+
+// returns the height of the subtree; leaf indices are relative to the level's first leaf
+int pw_build(int off, int n, int level, int leaf0, PwPlan& p, std::vector<PwTmpNode>& tmp, int depth) {
     if (depth > p.max_depth) p.max_depth = depth;
     if (n <= 128) {
         p.leaves.push_back({level, off, n});
-        p.prog.push_back(0);
-        return;
+        return 0;
     }
     int n2 = n / 2;
     n2 -= n2 % 8;
-    pw_build(off, n2, level, p, depth + 1);
-    pw_build(off + n2, n - n2, level, p, depth + 1);
-    p.prog.push_back(1);
+    const int a = (int)p.leaves.size() - leaf0;
+    const int hl = pw_build(off, n2, level, leaf0, p, tmp, depth + 1);
+    const int m = (int)p.leaves.size() - leaf0;
+    const int hr = pw_build(off + n2, n - n2, level, leaf0, p, tmp, depth + 1);
+    const int h = 1 + (hl > hr ? hl : hr);
+    tmp.push_back({a, m, h});
+    return h;
 }
 
 PwPlan make_pw_plan(const Pyramid& py) {
@@ -165,12 +181,17 @@ PwPlan make_pw_plan(const Pyramid& py) {
     for (int l = 1; l <= py.L; ++l) {
         PwLevel& lv = p.levels[l];
         lv.leaf0 = (int)p.leaves.size();
-        lv.prog0 = (int)p.prog.size();
+        lv.node0 = (int)p.nodes.size();
         lv.band = (long long)py.H[l] * py.W[l];
         lv.det_off = py.off[l];
-        pw_build(0, (int)lv.band, l, p, 1);
+        std::vector<PwTmpNode> tmp;
+        const int height = pw_build(0, (int)lv.band, l, lv.leaf0, p, tmp, 1);
         lv.n_leaf = (int)p.leaves.size() - lv.leaf0;
-        lv.n_prog = (int)p.prog.size() - lv.prog0;
+        lv.n_rounds = height;
+        for (int r = 1; r <= height && r <= PW_MAX_ROUNDS; ++r) {
+            for (const PwTmpNode& t : tmp) if (t.height == r) p.nodes.push_back({t.a, t.m});
+            lv.round_end[r - 1] = (int)p.nodes.size() - lv.node0;
+        }
     }
     return p;
 }
@@ -217,25 +238,30 @@ k_pw_leaves(const float* __restrict__ det, long long det_stride, const PwLeaf* _
     if (j == 0) leaf_sums[((size_t)si * 3 + b) * n_leaves + g] = res;
 }
 
-// One thread per (slice, level, band) replays the post-order combine program.
-__global__ void k_pw_combine(const unsigned char* __restrict__ prog, const PwLevel* __restrict__ levels,
-                             int L, int n_leaves, Dims d, const int* __restrict__ skip,
-                             const float* __restrict__ leaf_sums, WaveAcc* __restrict__ acc) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= d.n_sel * L * 3) return;
-    const int si = t / (L * 3), rem = t - si * L * 3;
-    const int l = rem / 3 + 1, b = rem - (l - 1) * 3;
+// One block per (slice, level, band): the pairwise tree is reduced in place, one round per tree
+// height (nodes of equal height are independent), exactly the additions numpy performs.
+__global__ void __launch_bounds__(NT)
+k_pw_combine(const PwNode* __restrict__ nodes, const PwLevel* __restrict__ levels, int L, int n_leaves,
+             Dims d, const int* __restrict__ skip, float* __restrict__ leaf_sums, WaveAcc* __restrict__ acc) {
+    const int si = blockIdx.y;
+    const int l = blockIdx.x / 3 + 1, b = blockIdx.x - (l - 1) * 3;
     if (skip && skip[slice_of(d.sel, si)]) return;
-    const PwLevel lv = levels[l];
-    const float* ls = leaf_sums + ((size_t)si * 3 + b) * n_leaves + lv.leaf0;
-    const unsigned char* pg = prog + lv.prog0;
-    float stack[40];
-    int sp = 0, next = 0;
-    for (int i = 0; i < lv.n_prog; ++i) {
-        if (pg[i] == 0) stack[sp++] = ls[next++];
-        else { --sp; stack[sp - 1] = __fadd_rn(stack[sp - 1], stack[sp]); }
+    __shared__ PwLevel lv;
+    if (threadIdx.x == 0) lv = levels[l];
+    __syncthreads();
+    float* ls = leaf_sums + ((size_t)si * 3 + b) * n_leaves + lv.leaf0;
+    const PwNode* nd = nodes + lv.node0;
+    int begin = 0;
+    for (int r = 0; r < lv.n_rounds; ++r) {
+        const int end = lv.round_end[r];
+        for (int i = begin + threadIdx.x; i < end; i += NT) {
+            const PwNode n = nd[i];
+            ls[n.a] = __fadd_rn(ls[n.a], ls[n.m]);
+        }
+        begin = end;
+        __syncthreads();
     }
-    acc[si].energy[l][b] = stack[0];
+    if (threadIdx.x == 0) acc[si].energy[l][b] = ls[0];
 }
 
 __global__ void k_wave_ranks(Dims d, int len, const WaveAcc* __restrict__ acc, int* __restrict__ ranks) {
@@ -387,7 +413,7 @@ k_haar_inv(const TA* __restrict__ ain, long long a_stride, int a_pitch, int hd, 
 struct WaveBufs {
     WaveAcc* acc; float* det; float* a0; float* a1; double* r0; double* r1;
     unsigned* l1; int* ranks; float* med; void* sel_ws; size_t sel_ws_bytes;
-    PwLeaf* pw_leaves; PwLevel* pw_levels; unsigned char* pw_prog; float* pw_sums;
+    PwLeaf* pw_leaves; PwLevel* pw_levels; PwNode* pw_nodes; float* pw_sums;
 };
 
 // upper bounds that depend only on the pyramid (the plan itself is built per call)
@@ -412,7 +438,7 @@ void carve(Arena& a, int n, int n_sel, const Pyramid& p, WaveBufs& b) {
     const size_t ml = pw_max_leaves(p);
     b.pw_leaves = a.take<PwLeaf>(ml);
     b.pw_levels = a.take<PwLevel>(MAXL + 2);
-    b.pw_prog = a.take<unsigned char>(2 * ml + 16);
+    b.pw_nodes = a.take<PwNode>(ml + 16);
     b.pw_sums = a.take<float>((size_t)n_sel * 3 * ml);
 }
 
@@ -498,15 +524,15 @@ int wavelet_denoise_run(const float* in, float* out, const Dims& d, int mode_har
     {
         const PwPlan& plan = cached_pw_plan(p);      // process-lifetime host copy: safe source for async copies
         const int n_leaves = (int)plan.leaves.size();
-        if ((size_t)n_leaves > pw_max_leaves(p) || plan.max_depth > 38)
+        if ((size_t)n_leaves > pw_max_leaves(p) || plan.max_depth > PW_MAX_ROUNDS - 2)
             return set_error(MDIMG_ERR_INVALID, "wavelet: pairwise plan exceeds its bounds (%d leaves, depth %d)", n_leaves, plan.max_depth);
         cudaMemcpyAsync(b.pw_leaves, plan.leaves.data(), sizeof(PwLeaf) * n_leaves, cudaMemcpyHostToDevice, stream);
         cudaMemcpyAsync(b.pw_levels, plan.levels.data(), sizeof(PwLevel) * plan.levels.size(), cudaMemcpyHostToDevice, stream);
-        cudaMemcpyAsync(b.pw_prog, plan.prog.data(), plan.prog.size(), cudaMemcpyHostToDevice, stream);
+        if (!plan.nodes.empty())
+            cudaMemcpyAsync(b.pw_nodes, plan.nodes.data(), sizeof(PwNode) * plan.nodes.size(), cudaMemcpyHostToDevice, stream);
         dim3 lgrid((n_leaves * 8 + NT - 1) / NT, d.n_sel, 3);
         MDIMG_LAUNCH k_pw_leaves<<<lgrid, NT, 0, stream>>>(b.det, p.det_per_slice, b.pw_leaves, b.pw_levels, n_leaves, d, skip, b.pw_sums);
-        const int nt = d.n_sel * p.L * 3;
-        MDIMG_LAUNCH k_pw_combine<<<(nt + 127) / 128, 128, 0, stream>>>(b.pw_prog, b.pw_levels, p.L, n_leaves, d, skip, b.pw_sums, b.acc);
+        MDIMG_LAUNCH k_pw_combine<<<dim3(p.L * 3, d.n_sel), NT, 0, stream>>>(b.pw_nodes, b.pw_levels, p.L, n_leaves, d, skip, b.pw_sums, b.acc);
     }
 
     // ---- sigma (finest 'dd' band) and thresholds ----

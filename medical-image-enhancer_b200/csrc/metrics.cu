@@ -287,11 +287,8 @@ k_db2_dd(const float* __restrict__ img, Dims d, int hd, int wd, float* __restric
     const float* src = img + (size_t)s * d.h * d.w;
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < SEL_L1_BINS; i += NT) hh[i] = 0;
-    for (int i = tid; i < DIN * DIN; i += NT) {
-        int r = i / DIN, c = i - r * DIN;
-        int gy = refl_sym(2 * oy0 - 2 + r, d.h), gx = refl_sym(2 * ox0 - 2 + c, d.w);
-        IN[r][c] = src[(size_t)gy * d.w + gx];
-    }
+    // 66 x 66 inputs starting two samples before (2*ox0, 2*oy0), half-sample symmetric border
+    load_tile<DIN, DIN, 2, 0>(src, d.h, d.w, 2 * ox0, 2 * oy0, [&](int r, int c, float v) { IN[r][c] = v; });
     __syncthreads();
     // axis 0: out[o] = ((f0*x[2o+1] + f1*x[2o]) + f2*x[2o-1]) + f3*x[2o-2]
     for (int i = tid; i < DT * DIN; i += NT) {

@@ -147,12 +147,63 @@ k_sel_scan1(Params P, Dims d) {
     }
 }
 
+// Per-element work of a refinement pass: level-1 bin -> one byte lookup; only elements of a bin
+// that holds an unresolved query (about 1 %) go on to the range tests and the histogram.
+template <bool ABS>
+__device__ __forceinline__ void refine_visit(float f, unsigned flag_sa, int nu,
+                                             const unsigned* __restrict__ ulo, const unsigned* __restrict__ uspan,
+                                             const int* __restrict__ ushift, unsigned* __restrict__ hbase, int lane) {
+    f = __fadd_rn(ABS ? fabsf(f) : f, 0.0f);
+    unsigned hit;      // shared-window address kept in a register: ptxas otherwise rebuilds it per element
+    asm("ld.shared.u8 %0, [%1];" : "=r"(hit) : "r"(flag_sa + (unsigned)sel_bin1(f)));
+    if (hit) {
+        const unsigned key = f2key(f);
+        for (int j = 0; j < nu; ++j) {
+            const unsigned off = key - ulo[j];
+            if (off <= uspan[j]) {
+                const unsigned slot = (unsigned)j * SEL_REFINE_BINS + (off >> ushift[j]);
+                const unsigned peers = __match_any_sync(__activemask(), slot);
+                if (lane == __ffs(peers) - 1) atomicAdd(hbase + slot, (unsigned)__popc(peers));
+                break;
+            }
+        }
+    }
+}
+
+template <bool ABS>
+__device__ __forceinline__ void refine_stream(const float* __restrict__ v, int len, int tid, int nthr,
+                                              unsigned flag_sa, int nu,
+                                              const unsigned* __restrict__ ulo, const unsigned* __restrict__ uspan,
+                                              const int* __restrict__ ushift, unsigned* __restrict__ hbase, int lane) {
+#define MDIMG_VISIT(x) refine_visit<ABS>(x, flag_sa, nu, ulo, uspan, ushift, hbase, lane)
+    if ((((uintptr_t)v) & 15) == 0) {
+        const int n4 = len >> 2;
+        const float4* v4 = reinterpret_cast<const float4*>(v);
+        int i = tid;
+        for (; i + 3 * nthr < n4; i += 4 * nthr) {                 // four independent 128-bit loads in flight
+            const float4 a = v4[i], b = v4[i + nthr], c = v4[i + 2 * nthr], e = v4[i + 3 * nthr];
+            MDIMG_VISIT(a.x); MDIMG_VISIT(a.y); MDIMG_VISIT(a.z); MDIMG_VISIT(a.w);
+            MDIMG_VISIT(b.x); MDIMG_VISIT(b.y); MDIMG_VISIT(b.z); MDIMG_VISIT(b.w);
+            MDIMG_VISIT(c.x); MDIMG_VISIT(c.y); MDIMG_VISIT(c.z); MDIMG_VISIT(c.w);
+            MDIMG_VISIT(e.x); MDIMG_VISIT(e.y); MDIMG_VISIT(e.z); MDIMG_VISIT(e.w);
+        }
+        for (; i < n4; i += nthr) {
+            const float4 q = v4[i];
+            MDIMG_VISIT(q.x); MDIMG_VISIT(q.y); MDIMG_VISIT(q.z); MDIMG_VISIT(q.w);
+        }
+        for (int k = (n4 << 2) + tid; k < len; k += nthr) MDIMG_VISIT(v[k]);
+    } else {
+        for (int i = tid; i < len; i += nthr) MDIMG_VISIT(v[i]);
+    }
+#undef MDIMG_VISIT
+}
+
 // One refinement pass (+ the slice's scan, done by the last block to finish).
 __global__ void __launch_bounds__(ST)
 k_sel_refine(Params P, Dims d) {
     __shared__ unsigned ulo[SEL_MAX_Q], uspan[SEL_MAX_Q];
     __shared__ int ushift[SEL_MAX_Q];
-    __shared__ unsigned bitmap[SEL_L1_BINS / 32];
+    __shared__ __align__(16) unsigned char flag[SEL_L1_BINS];
     __shared__ int nu_s, last_s;
     __shared__ unsigned cum[SEL_REFINE_BINS];
     __shared__ unsigned warp_tot[ST / 32];
@@ -161,7 +212,8 @@ k_sel_refine(Params P, Dims d) {
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
     const SelState* gst = J.states + si;
-    if (threadIdx.x < SEL_L1_BINS / 32) bitmap[threadIdx.x] = 0;
+    reinterpret_cast<unsigned*>(flag)[threadIdx.x] = 0;           // 256 threads x 4 bytes = SEL_L1_BINS
+    static_assert(SEL_L1_BINS == ST * 4, "flag table is cleared one word per thread");
     if (threadIdx.x == 0) nu_s = gst->nuniq;
     __syncthreads();
     const int nu = nu_s;
@@ -170,52 +222,17 @@ k_sel_refine(Params P, Dims d) {
         ulo[threadIdx.x] = gst->ulo[threadIdx.x];
         uspan[threadIdx.x] = gst->uspan[threadIdx.x];
         ushift[threadIdx.x] = gst->ushift[threadIdx.x];
-        const int bin = gst->ubin[threadIdx.x];
-        atomicOr(&bitmap[bin >> 5], 1u << (bin & 31));
+        flag[gst->ubin[threadIdx.x]] = 1;
     }
     __syncthreads();
     const float* v = J.vals + (size_t)((J.opts & SEL_COMPACT) ? si : s) * J.stride;
-    const bool use_abs = (J.opts & SEL_ABS) != 0;
     unsigned* hbase = J.hist + (size_t)si * SEL_MAX_Q * SEL_REFINE_BINS;
     const int lane = threadIdx.x & 31;
-    const int len = J.len;
-
-    auto visit = [&](float f) {
-        f = __fadd_rn(use_abs ? fabsf(f) : f, 0.0f);
-        const int bin = sel_bin1(f);
-        if ((bitmap[bin >> 5] >> (bin & 31)) & 1u) {
-            const unsigned key = f2key(f);
-            for (int j = 0; j < nu; ++j) {
-                const unsigned off = key - ulo[j];
-                if (off <= uspan[j]) {
-                    const unsigned slot = (unsigned)j * SEL_REFINE_BINS + (off >> ushift[j]);
-                    const unsigned peers = __match_any_sync(__activemask(), slot);
-                    if (lane == __ffs(peers) - 1) atomicAdd(hbase + slot, (unsigned)__popc(peers));
-                    break;
-                }
-            }
-        }
-    };
     const int tid = blockIdx.x * ST + threadIdx.x, nthr = gridDim.x * ST;
-    if ((((uintptr_t)v) & 15) == 0) {
-        const int n4 = len >> 2;
-        const float4* v4 = reinterpret_cast<const float4*>(v);
-        int i = tid;
-        for (; i + 3 * nthr < n4; i += 4 * nthr) {                 // four independent 128-bit loads in flight
-            const float4 a = v4[i], b = v4[i + nthr], c = v4[i + 2 * nthr], e = v4[i + 3 * nthr];
-            visit(a.x); visit(a.y); visit(a.z); visit(a.w);
-            visit(b.x); visit(b.y); visit(b.z); visit(b.w);
-            visit(c.x); visit(c.y); visit(c.z); visit(c.w);
-            visit(e.x); visit(e.y); visit(e.z); visit(e.w);
-        }
-        for (; i < n4; i += nthr) {
-            const float4 q = v4[i];
-            visit(q.x); visit(q.y); visit(q.z); visit(q.w);
-        }
-        for (int k = (n4 << 2) + tid; k < len; k += nthr) visit(v[k]);
-    } else {
-        for (int i = tid; i < len; i += nthr) visit(v[i]);
-    }
+    unsigned flag_sa;   // opaque copy: ptxas would otherwise rematerialise the window base per element
+    asm volatile("mov.u32 %0, %1;" : "=r"(flag_sa) : "r"((unsigned)__cvta_generic_to_shared(flag)));
+    if (J.opts & SEL_ABS) refine_stream<true>(v, J.len, tid, nthr, flag_sa, nu, ulo, uspan, ushift, hbase, lane);
+    else refine_stream<false>(v, J.len, tid, nthr, flag_sa, nu, ulo, uspan, ushift, hbase, lane);
 
     // ---- last block of this slice: scan the digit histograms, narrow the ranges ----
     __threadfence();

@@ -6,7 +6,7 @@
 // Range select on the order-preserving uint32 image of the float bits:
 //   level 1  a 1024-bin histogram over a monotone map of the value (sel_bin1: uniform bins over
 //            (0, 1), where this pipeline's pixels, |gradients| and |wavelet coefficients| live; one
-//            bin each for negatives, exact zero and values >= 1).  It is accumulated by the kernel
+//            bin each for negatives, exact zero and values > 1).  It is accumulated by the kernel
 //            that PRODUCES the data, so it costs no extra read.  A query whose bin holds a single key
 //            (exact zero: CT air) is resolved here.
 //   refine   up to three passes; each histograms, for the few elements that fall into the key range
@@ -31,12 +31,13 @@ constexpr int SEL_ABS = 2;       // select on |v| (the level-1 histogram must be
 // Selection key: -0.0 is folded into +0.0 so that "exactly zero" is a single key.
 __device__ __forceinline__ unsigned sel_key(float v) { return f2key(__fadd_rn(v, 0.0f)); }
 
-// Level-1 bin, monotone non-decreasing in the value: 0 negatives, 1 zero, 2..1022 uniform over
-// (0, 1), 1023 values >= 1 (NaNs land in bin 1 / 1023 and are never selected).
+// Level-1 bin, monotone non-decreasing in the value and branch-free: 0 negatives, 1 zero,
+// 2..1022 uniform over (0, 1] (bin = 1 + ceil(1021 v)), 1023 above.  float->int conversion
+// saturates; NaNs land in bin 1 and are never selected.
 __device__ __forceinline__ int sel_bin1(float v) {
-    if (!(v > 0.0f)) return v < 0.0f ? 0 : 1;
-    const float t = __fmul_rn(v, 1021.0f);
-    return t >= 1021.0f ? 1023 : 2 + (int)t;
+    const int c = __float2int_ru(__fmul_rn(v, 1021.0f));
+    const int b = 1 + min(c, 1022);
+    return v < 0.0f ? 0 : b;
 }
 #endif
 

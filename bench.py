@@ -236,11 +236,13 @@ def run_gpu(args) -> None:
             dist.all_gather_into_tensor(gathered, rows)
         return res
 
-    e2e_chunk = max(1, min(chunk, n // 4))     # >= 4 chunks so copies overlap compute
+    # several chunks per stack so copies overlap compute; the first copy-in and the last copy-out
+    # cannot overlap anything, so the chunks of the end-to-end path are smaller than the resident ones
+    e2e_chunk = args.e2e_chunk or max(1, min(chunk, n // 8))
 
     def step_e2e():
         out, res = process_stack_host(stack, plan, chunk=e2e_chunk, ops=ops, pinned_in=pinned_in,
-                                      pinned_out=pinned_out)
+                                      pinned_out=pinned_out, workers=args.workers)
         if world > 1:
             rows = torch.from_numpy(res.packed).to(device)
             dist.all_gather_into_tensor(gathered, rows)
@@ -363,6 +365,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slices", type=int, default=1024, help="slices per GPU")
     ap.add_argument("--chunk", type=int, default=0, help="slices per chunk (0 = auto)")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="slices per chunk of the end-to-end leg (0 = auto)")
     ap.add_argument("--workers", type=int, default=2, help="host threads / CUDA streams driving chunks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -175,10 +175,13 @@ def _worker_streams(device: torch.device, count: int):
 
 def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
                        out_host: Optional[np.ndarray] = None, ops: Optional[StackOps] = None,
-                       pinned_in: Optional[torch.Tensor] = None, pinned_out: Optional[torch.Tensor] = None):
+                       pinned_in: Optional[torch.Tensor] = None, pinned_out: Optional[torch.Tensor] = None,
+                       workers: int = 2):
     """End-to-end form with HOST buffers: per chunk, host->device copy of the raw slices, the whole
     pipeline on the GPU, device->host copy of the enhanced slices and of the result rows.
-    Copies of chunk k+1 / k-1 overlap the compute of chunk k on side streams.
+    `workers` host threads each drive every workers-th chunk with their own compute / copy-in /
+    copy-out streams: copies of one chunk overlap the compute of the others, and the host round
+    trips inside a chunk (TV live-slice polls, safeguard decisions) never leave the GPU idle.
 
     raw_host: [N, H, W] uint16 or float32 numpy array (ideally backed by pinned memory).
     Returns (enhanced float32 host array, StackResult without device pixels)."""
@@ -195,44 +198,79 @@ def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
     else:
         out_t = torch.from_numpy(out_host)
     packed_host = torch.empty((n, PACK_COLS), dtype=torch.float64, pin_memory=True)
-    main = torch.cuda.current_stream(dev)
-    copy_in = torch.cuda.Stream(dev)
-    copy_out = torch.cuda.Stream(dev)
-    labels: List[List[str]] = []
     spans = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
-    staged = {}
+    workers = max(1, min(workers, len(spans)))
+    labels: List[Optional[List[List[str]]]] = [None] * len(spans)
+    caller = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(caller)
+    errors: List[BaseException] = []
 
-    def stage(i):
-        a, b = spans[i]
-        with torch.cuda.stream(copy_in):
-            t = src_t[a:b].to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_in)
-        staged[i] = (t, ev)
+    def worker(k: int) -> None:
+        try:
+            with torch.cuda.device(dev):
+                main, copy_in, copy_out = _host_streams(dev, k)
+                mine = list(range(k, len(spans), workers))
+                staged = {}
 
-    if spans:
-        stage(0)
-    pending = []
-    for i, (a, b) in enumerate(spans):
-        if i + 1 < len(spans):
-            stage(i + 1)
-        raw_d, ev = staged.pop(i)
-        main.wait_event(ev)
-        raw_d.record_stream(main)
-        enh, packed, lab = process_chunk(ops, raw_d, plan, True)
-        done = torch.cuda.Event()
-        done.record(main)
-        with torch.cuda.stream(copy_out):
-            copy_out.wait_event(done)
-            out_t[a:b].copy_(enh, non_blocking=True)
-            packed_host[a:b].copy_(packed, non_blocking=True)
-            enh.record_stream(copy_out)
-            packed.record_stream(copy_out)
-        labels.extend(lab)
-    copy_out.synchronize()
-    main.synchronize()
-    res = StackResult(enhanced=None, packed=packed_host.numpy().copy(), labels=labels)
+                def stage(i):
+                    a, b = spans[i]
+                    with torch.cuda.stream(copy_in):
+                        t = src_t[a:b].to(dev, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_in)
+                    staged[i] = (t, ev)
+
+                copy_in.wait_event(ready)
+                main.wait_event(ready)
+                if mine:
+                    stage(mine[0])
+                with torch.cuda.stream(main):
+                    for j, i in enumerate(mine):
+                        if j + 1 < len(mine):
+                            stage(mine[j + 1])
+                        a, b = spans[i]
+                        raw_d, ev = staged.pop(i)
+                        main.wait_event(ev)
+                        raw_d.record_stream(main)
+                        enh, packed, lab = process_chunk(ops, raw_d, plan, True)
+                        done = torch.cuda.Event()
+                        done.record(main)
+                        with torch.cuda.stream(copy_out):
+                            copy_out.wait_event(done)
+                            out_t[a:b].copy_(enh, non_blocking=True)
+                            packed_host[a:b].copy_(packed, non_blocking=True)
+                            enh.record_stream(copy_out)
+                            packed.record_stream(copy_out)
+                        labels[i] = lab
+                copy_out.synchronize()
+                main.synchronize()
+        except BaseException as exc:  # noqa: BLE001 - re-raised on the caller's thread
+            errors.append(exc)
+
+    if workers == 1:
+        worker(0)
+    else:
+        threads = [threading.Thread(target=worker, args=(k,), daemon=True) for k in range(workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    flat = [lab for part in labels for lab in (part or [])]
+    res = StackResult(enhanced=None, packed=packed_host.numpy().copy(), labels=flat)
     return out_t.numpy(), res
+
+
+_host_stream_cache: dict = {}
+
+
+def _host_streams(device: torch.device, k: int):
+    key = (device.index, k)
+    if key not in _host_stream_cache:
+        _host_stream_cache[key] = tuple(torch.cuda.Stream(device) for _ in range(3))
+    return _host_stream_cache[key]
 
 
 def score_plans(images: torch.Tensor, plans, ops: Optional[StackOps] = None):

@@ -1,0 +1,97 @@
+"""The other BASELINE.json configurations (parity-tested in tests/test_gpu_large.py), timed on one GPU:
+  C3  64 synthetic 3000x3000 uint16 radiographs, P_cr (CLAHE + unsharp heavy) + metrics + validation
+  C5  metrics-only sweep (compute_metrics + compute_validation against a gamma-0.9 copy), 256^2 .. 4096^2,
+      batches of ~256 Mpx per point
+Prints one JSON object; CUDA-event timing after a warm-up pass, inputs resident in HBM.
+    python tools/bench_configs.py [c3_images] [c5_mpx]
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from mdimg_b200 import synth  # noqa: E402
+from mdimg_b200.batch import process_stack  # noqa: E402
+from mdimg_b200.engine import Engine  # noqa: E402
+from mdimg_b200.stack import get_ops  # noqa: E402
+
+PEAK = 6552.6
+try:
+    PEAK = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+except Exception:  # noqa: BLE001
+    pass
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def main():
+    n3 = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    mpx5 = float(sys.argv[2]) if len(sys.argv) > 2 else 256.0
+    ops = get_ops()
+    out = {"hbm_peak_gbs": PEAK}
+
+    # ---- C3 ----
+    base = [synth.radiograph(2000 + i) for i in range(min(n3, 8))]
+    raw = np.stack([base[i % len(base)] for i in range(n3)])
+    dev = torch.from_numpy(raw.view(np.int16)).to(ops.device)
+    plan = synth.plan_cr()
+    ms = timed(lambda: process_stack(dev, plan, chunk=16, ops=ops), reps=2)
+    px = float(n3) * 3000 * 3000
+    # P_cr = 72 B/px algorithmic
+    out["C3"] = {"images": n3, "size": 3000, "ms": ms, "mpx_per_s": px / ms / 1e3, "images_per_s": n3 / ms * 1e3,
+                 "algorithmic_GBps": 72 * px / ms / 1e6, "frac_of_hbm_peak": 72 * px / ms / 1e6 / PEAK,
+                 "note": f"{len(base)} distinct images repeated to {n3}; chunk 16 images"}
+    del dev
+    torch.cuda.empty_cache()
+
+    # ---- C5 ----
+    eng = Engine(ops)
+    out["C5"] = []
+    for k, size in enumerate((256, 512, 1024, 2048, 4096)):
+        n = max(1, int(round(mpx5 * 1e6 / (size * size))))
+        distinct = min(n, 8)
+        imgs = np.stack([synth.unit_image(4000 + k * 16 + i, size) for i in range(distinct)])
+        x = torch.from_numpy(np.ascontiguousarray(imgs[np.arange(n) % distinct])).to(ops.device)
+        y = torch.empty_like(x)
+        ops.gamma(x, y, 0.9)
+
+        def metrics_only():
+            return ops.metrics(x)
+
+        def validation():
+            rb, ra, fr = eng.validation_rows(x, y)
+            return rb.cpu()
+
+        ms_m = timed(metrics_only)
+        ms_v = timed(validation)
+        px = float(n) * size * size
+        out["C5"].append({"size": size, "images": n, "compute_metrics_ms": ms_m,
+                          "compute_metrics_mpx_per_s": px / ms_m / 1e3,
+                          "compute_metrics_GBps_alg4": 4 * px / ms_m / 1e6,
+                          "compute_metrics_frac": 4 * px / ms_m / 1e6 / PEAK,
+                          "compute_validation_ms": ms_v, "compute_validation_mpx_per_s": px / ms_v / 1e3,
+                          "compute_validation_GBps_alg16": 16 * px / ms_v / 1e6,
+                          "compute_validation_frac": 16 * px / ms_v / 1e6 / PEAK})
+        del x, y
+        torch.cuda.empty_cache()
+    print(json.dumps(out, indent=1))
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / "bench_configs.json").write_text(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

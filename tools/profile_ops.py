@@ -60,9 +60,27 @@ def main():
         launches = ops.lib.mdimg_launch_count() - l0
         print(f"\n== chunk {chunk}: {n} slices, device {total:.1f} ms, wall {wall:.1f} ms, "
               f"{n*512*512/total/1e3:.1f} Mpx/s, {launches} launches, sum(ops) {sum(agg.values()):.1f} ms")
+        it_mean = float(res.tv_iterations.mean())
+        # algorithmic bytes per pixel and call of every operator
+        alg = {"mdimg_normalize_u16": 8, "mdimg_metrics": 4, "mdimg_fullref": 8, "mdimg_wavelet_denoise": 12,
+               "mdimg_light_denoise": 16, "mdimg_clahe": 16, "mdimg_gamma": 8, "mdimg_unsharp": 8,
+               "mdimg_bilateral": 8, "mdimg_tv_chambolle": 20 * it_mean + 4, "mdimg_clip01": 8,
+               "mdimg_estimate_sigma": 4, "mdimg_quality": 4}
+        peak = 6552.6
+        try:
+            peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+        except Exception:  # noqa: BLE001
+            pass
+        px = n * 512 * 512
         for name, ms in sorted(agg.items(), key=lambda kv: -kv[1]):
+            b = alg.get(name)
+            roof = ""
+            if b:
+                n_chunks = max(1, -(-n // chunk))
+                gbs = b * px * (cnt[name] / n_chunks) / (ms / 1e3) / 1e9     # every call covers one chunk
+                roof = f"  alg {b:6.1f} B/px  {gbs:7.0f} GB/s  {100 * gbs / peak:5.1f}% of HBM peak"
             print(f"   {name:28s} {ms:9.2f} ms  {100*ms/total:5.1f}%  calls {cnt[name]:5d}  "
-                  f"{ms/ n * 1e3:8.1f} us/slice")
+                  f"{ms/ n * 1e3:8.1f} us/slice{roof}")
         report[chunk] = {"total_ms": total, "wall_ms": wall, "launches": int(launches),
                          "ops": {k: v for k, v in agg.items()},
                          "tv_iters_mean": float(res.tv_iterations.mean())}

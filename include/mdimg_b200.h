@@ -131,6 +131,13 @@ int mdimg_wavelet_denoise(const float* in, float* out, int n, int h, int w, cons
 int mdimg_clahe(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
                 double clip_limit, int kernel_size, int32_t* status, void* ws, size_t ws_bytes,
                 void* stream);
+/* equalize_adapthist followed directly by adjust_gamma (pipeline/enhancement.py:277-286 when the
+ * plan holds both "clahe" and "gamma"): the power is folded into CLAHE's final 16384-level
+ * stretch table, so the step costs no pass of its own.  gamma == 1 is mdimg_clahe.  Same workspace
+ * as mdimg_clahe (MDIMG_OP_CLAHE). */
+int mdimg_clahe_gamma(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                      double clip_limit, int kernel_size, double gamma, int32_t* status, void* ws,
+                      size_t ws_bytes, void* stream);
 /* exposure.adjust_gamma(image, gamma) (pipeline/enhancement.py:194,197,284,336).
  * neg_flag: device int32[n]; 1 where a slice holds a negative pixel (ValueError in the reference).
  * assume_nonneg != 0 skips the min/max pre-pass (caller guarantees non-negative input). */

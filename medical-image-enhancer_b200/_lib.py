@@ -48,6 +48,7 @@ PROTOTYPES = {
     "mdimg_fullref": (_i, [_p, _p, *_IMG, _p, *_WS]),
     "mdimg_wavelet_denoise": (_i, [_p, _p, *_IMG, _i, _p, _d, _p, *_WS]),
     "mdimg_clahe": (_i, [_p, _p, *_IMG, _d, _i, _p, *_WS]),
+    "mdimg_clahe_gamma": (_i, [_p, _p, *_IMG, _d, _i, _d, _p, *_WS]),
     "mdimg_gamma": (_i, [_p, _p, *_IMG, _d, _i, _p, *_WS]),
     "mdimg_unsharp": (_i, [_p, _p, *_IMG, C.POINTER(_d), _i, _d, _i, *_WS]),
     "mdimg_light_denoise": (_i, [_p, _p, *_IMG, _d, _p, *_WS]),

@@ -226,9 +226,9 @@ int mdimg_wavelet_denoise(const float* in, float* out, int n, int h, int w, cons
                                (cudaStream_t)stream);
 }
 
-int mdimg_clahe(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
-                double clip_limit, int kernel_size, int32_t* status, void* ws, size_t ws_bytes,
-                void* stream) {
+int mdimg_clahe_gamma(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                      double clip_limit, int kernel_size, double gamma, int32_t* status, void* ws,
+                      size_t ws_bytes, void* stream) {
     if (bad_dims(n, h, w, sel, n_sel)) return MDIMG_ERR_INVALID;
     Dims d = make_dims(n, h, w, sel, n_sel);
     Arena a(ws, ws_bytes);
@@ -236,8 +236,15 @@ int mdimg_clahe(const float* in, float* out, int n, int h, int w, const int32_t*
     if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "clahe: workspace too small");
     int rc = minmax_f32_run(in, d, mm, (cudaStream_t)stream);
     if (rc) return rc;
-    return clahe_run(in, out, d, clip_limit, kernel_size, mm, status, (char*)ws + a.off,
+    return clahe_run(in, out, d, clip_limit, kernel_size, gamma, mm, status, (char*)ws + a.off,
                      ws_bytes - a.off, (cudaStream_t)stream);
+}
+
+int mdimg_clahe(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                double clip_limit, int kernel_size, int32_t* status, void* ws, size_t ws_bytes,
+                void* stream) {
+    return mdimg_clahe_gamma(in, out, n, h, w, sel, n_sel, clip_limit, kernel_size, 1.0, status, ws,
+                             ws_bytes, stream);
 }
 
 int mdimg_gamma(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,

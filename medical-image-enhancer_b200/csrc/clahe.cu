@@ -14,7 +14,8 @@
 //
 // Kernels: k_clahe_hist (one warp per contextual region: quantise, histogram in shared memory,
 // clip/redistribute, CDF -> uint16 LUT; also stores the 8-bit bin image), k_clahe_blend (bilinear
-// LUT blend -> uint16 + per-slice min/max), k_clahe_final (float32 stretch).
+// LUT blend -> uint16 + per-slice min/max), k_clahe_lut + k_clahe_final (float32 stretch, optionally
+// followed by adjust_gamma, through a 16384-level table).
 #include "enhance.cuh"
 
 namespace mdimg {
@@ -218,34 +219,70 @@ k_clahe_blend(Dims d, ClaheGeom g, SliceRange* __restrict__ rng, const int* __re
     }
 }
 
+// The blended image holds at most 16384 distinct levels, so the final float32 stretch
+// (v - vmin) / (vmax - vmin) -- and an adjust_gamma that directly follows CLAHE in the plan
+// (pipeline/enhancement.py:277-286) -- is a per-slice table: one IEEE division (and one correctly
+// rounded power) per LEVEL instead of per pixel, then a pure gather.
+constexpr int NLEVELS = 16384;
+
 __global__ void __launch_bounds__(NT)
-k_clahe_final(Dims d, const SliceRange* __restrict__ rng, const int* __restrict__ status,
-              const uint16_t* __restrict__ vin, float* __restrict__ out) {
+k_clahe_lut(Dims d, const SliceRange* __restrict__ rng, const int* __restrict__ status, double gamma,
+            float* __restrict__ lut) {
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    if (status[s]) return;
+    const unsigned vmin = rng[si].vmin, vmax = rng[si].vmax;
+    const int v = blockIdx.x * NT + threadIdx.x;
+    if (v >= NLEVELS) return;
+    const float lo = (float)vmin;
+    const float den = (float)((double)vmax - (double)vmin);
+    const float f = (float)v;
+    float r;
+    if (vmin != vmax) r = __fdiv_rn(__fsub_rn(f, lo), den);
+    else r = fminf(fmaxf(f, 0.0f), 1.0f);
+    if (gamma != 1.0 && v >= (int)vmin && v <= (int)vmax) r = (float)pow((double)r, gamma);   // as GammaF (pointwise.cu)
+    lut[(size_t)si * NLEVELS + v] = r;
+}
+
+__global__ void __launch_bounds__(NT)
+k_clahe_final(Dims d, const int* __restrict__ status, const uint16_t* __restrict__ vin,
+              const float* __restrict__ lut, float* __restrict__ out) {
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
     if (status[s]) return;
     const long long len = d.px();
     const uint16_t* v = vin + (size_t)si * len;
     float* o = out + (size_t)s * len;
-    const unsigned vmin = rng[si].vmin, vmax = rng[si].vmax;
-    const float lo = (float)vmin;
-    const float den = (float)((double)vmax - (double)vmin);
-    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < len; i += (long long)gridDim.x * NT) {
-        const float f = (float)v[i];
-        float r;
-        if (vmin != vmax) r = __fdiv_rn(__fsub_rn(f, lo), den);
-        else r = fminf(fmaxf(f, 0.0f), 1.0f);
-        o[i] = r;
+    const float* L = lut + (size_t)si * NLEVELS;
+    const long long tid = (long long)blockIdx.x * NT + threadIdx.x, nthr = (long long)gridDim.x * NT;
+    if (((((uintptr_t)v) | ((uintptr_t)o)) & 15) == 0) {
+        const long long n8 = len >> 3;
+        const uint4* v8 = reinterpret_cast<const uint4*>(v);
+        float4* o4 = reinterpret_cast<float4*>(o);
+        for (long long i = tid; i < n8; i += nthr) {
+            const uint4 q = v8[i];
+            float4 a, b;
+            a.x = __ldg(L + (q.x & 0xffffu)); a.y = __ldg(L + (q.x >> 16));
+            a.z = __ldg(L + (q.y & 0xffffu)); a.w = __ldg(L + (q.y >> 16));
+            b.x = __ldg(L + (q.z & 0xffffu)); b.y = __ldg(L + (q.z >> 16));
+            b.z = __ldg(L + (q.w & 0xffffu)); b.w = __ldg(L + (q.w >> 16));
+            o4[2 * i] = a;
+            o4[2 * i + 1] = b;
+        }
+        for (long long i = (n8 << 3) + tid; i < len; i += nthr) o[i] = __ldg(L + v[i]);
+    } else {
+        for (long long i = tid; i < len; i += nthr) o[i] = __ldg(L + v[i]);
     }
 }
 
-struct ClaheBufs { SliceRange* rng; uint8_t* bins; uint16_t* maps; uint16_t* v; };
+struct ClaheBufs { SliceRange* rng; uint8_t* bins; uint16_t* maps; uint16_t* v; float* lut; };
 
 void carve(Arena& a, int n_sel, int h, int w, int nty, int ntx, ClaheBufs& b) {
     b.rng = a.take<SliceRange>(n_sel);
     b.bins = a.take<uint8_t>((size_t)n_sel * h * w);
     b.maps = a.take<uint16_t>((size_t)n_sel * nty * ntx * NBINS);
     b.v = a.take<uint16_t>((size_t)n_sel * h * w);
+    b.lut = a.take<float>((size_t)n_sel * NLEVELS);
 }
 
 inline void geom(int h, int w, int k, double clip_limit, ClaheGeom& g) {
@@ -276,11 +313,12 @@ size_t clahe_workspace_bytes(int n, int n_sel, int h, int w, int kernel_size) {
     return a.off;
 }
 
-int clahe_run(const float* in, float* out, const Dims& d, double clip_limit, int kernel_size,
+int clahe_run(const float* in, float* out, const Dims& d, double clip_limit, int kernel_size, double gamma,
               const uint2* mm, int* status, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (d.n_sel == 0) return MDIMG_OK;
     if (kernel_size < 1 || kernel_size > 48)
         return set_error(MDIMG_ERR_INVALID, "clahe: kernel_size %d outside [1, 48]", kernel_size);
+    if (!(gamma >= 0.0)) return set_error(MDIMG_ERR_INVALID, "Gamma should be a non-negative real number.");
     ClaheGeom g;
     geom(d.h, d.w, kernel_size, clip_limit, g);
     Arena a(ws, ws_bytes);
@@ -295,7 +333,8 @@ int clahe_run(const float* in, float* out, const Dims& d, double clip_limit, int
     long long len = d.px();
     int fb = (int)((len + NT * 8 - 1) / (NT * 8));
     if (fb > 4096) fb = 4096;
-    MDIMG_LAUNCH k_clahe_final<<<dim3(fb, d.n_sel), NT, 0, stream>>>(d, b.rng, status, b.v, out);
+    MDIMG_LAUNCH k_clahe_lut<<<dim3(NLEVELS / NT, d.n_sel), NT, 0, stream>>>(d, b.rng, status, gamma, b.lut);
+    MDIMG_LAUNCH k_clahe_final<<<dim3(fb, d.n_sel), NT, 0, stream>>>(d, status, b.v, b.lut, out);
     return check_launch("clahe");
 }
 

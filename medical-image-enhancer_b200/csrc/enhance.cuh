@@ -40,7 +40,8 @@ int unsharp_run(const float* in, float* out, const Dims& d, const double* weight
 // ---- clahe.cu ------------------------------------------------------------------------------
 size_t clahe_workspace_bytes(int n, int n_sel, int h, int w, int kernel_size);
 // status: device [n] int; 1 = input outside [-1, 1] (the reference raises ValueError).
-int clahe_run(const float* in, float* out, const Dims& d, double clip_limit, int kernel_size,
+// gamma != 1: exposure.adjust_gamma applied to the CLAHE result in the same final pass.
+int clahe_run(const float* in, float* out, const Dims& d, double clip_limit, int kernel_size, double gamma,
               const uint2* mm, int* status, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // ---- wavelet.cu ----------------------------------------------------------------------------

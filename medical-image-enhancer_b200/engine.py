@@ -165,10 +165,15 @@ class Engine:
             ops.wavelet_denoise(cur, cur, mode=q.dn_mode, sel=sel)
             state["nonneg"] = False
         elif name == "clahe":
-            status = ops.clahe(cur, cur, q.clip_limit, q.tile_size, sel=sel)
+            # an adjust_gamma that directly follows CLAHE is folded into CLAHE's final table pass
+            g = q.gamma if state.get("fuse_gamma") else 1.0
+            status = ops.clahe(cur, cur, q.clip_limit, q.tile_size, sel=sel, gamma=g)
             self._raise_if(status, "Images of type float must be between -1 and 1.", state)
             state["nonneg"] = True
+            state["gamma_done"] = g != 1.0
         elif name == "gamma":
+            if state.pop("gamma_done", False):      # already applied inside the CLAHE call
+                return cur, tmp
             neg = ops.gamma(cur, cur, q.gamma, assume_nonneg=state["nonneg"], sel=sel)
             if not state["nonneg"]:
                 self._raise_if(neg, "Image Correction methods work correctly only on images with "
@@ -258,7 +263,9 @@ class Engine:
         plan_ops = [op.lower().strip() for op in plan.recommended_ops]
         cur = image.clone()
         tmp = torch.empty_like(image)
-        state = {"nonneg": False, "tv_iters": None, "on_error": on_error}
+        state = {"nonneg": False, "tv_iters": None, "on_error": on_error,
+                 # fixed step order: "gamma" always comes right after "clahe" when both are enabled
+                 "fuse_gamma": "clahe" in plan_ops and "gamma" in plan_ops and self._enabled("gamma", q)}
         common: List[str] = []
         for name in _STEP_ORDER:   # fixed order, gated by membership
             if name in plan_ops and self._enabled(name, q):

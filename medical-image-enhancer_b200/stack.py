@@ -225,15 +225,16 @@ class StackOps:
                    ws, wsb, self._stream())
         return dst
 
-    def clahe(self, src, dst, clip_limit: float, kernel_size: int, sel=None) -> torch.Tensor:
-        """Returns the per-slice status tensor (1 = input outside [-1, 1])."""
+    def clahe(self, src, dst, clip_limit: float, kernel_size: int, sel=None, gamma: float = 1.0) -> torch.Tensor:
+        """Returns the per-slice status tensor (1 = input outside [-1, 1]).  gamma != 1 folds an
+        adjust_gamma that directly follows CLAHE into its final pass."""
         n, h, w = self._img(src).shape
         self._img(dst)
         status = torch.zeros((n,), dtype=torch.int32, device=self.device)
         ws, wsb = self._ws_for(_lib.OP_CLAHE, n, h, w, int(kernel_size))
         sp, ns = self._sel(sel)
-        self._call(self.lib.mdimg_clahe, self._ptr(src), self._ptr(dst), n, h, w, sp, ns,
-                   float(clip_limit), int(kernel_size), self._ptr(status), ws, wsb, self._stream())
+        self._call(self.lib.mdimg_clahe_gamma, self._ptr(src), self._ptr(dst), n, h, w, sp, ns,
+                   float(clip_limit), int(kernel_size), float(gamma), self._ptr(status), ws, wsb, self._stream())
         return status
 
     def gamma(self, src, dst, gamma: float, assume_nonneg: bool = False, sel=None) -> torch.Tensor:

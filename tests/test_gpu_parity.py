@@ -157,6 +157,23 @@ def test_clahe_constant_image(ops, dev):
 
 
 @pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("g", [0.95, 1.3])
+def test_clahe_with_folded_gamma_equals_the_two_separate_steps(ops, dev, images, name, g):
+    """mdimg_clahe_gamma == mdimg_clahe followed by mdimg_gamma, bit for bit (same float32 stretch,
+    same correctly rounded power, evaluated per level instead of per pixel)."""
+    im = images[name]
+    x = dev(im)
+    fused = torch.empty_like(x)
+    ops.clahe(x, fused, 0.015, 16, gamma=g)
+    two = torch.empty_like(x)
+    ops.clahe(x, two, 0.015, 16)
+    ops.gamma(two, two, g, assume_nonneg=True)
+    np.testing.assert_array_equal(host(fused), host(two))
+    ref = oex.adjust_gamma(oex.equalize_adapthist(im, kernel_size=16, clip_limit=0.015), g)
+    assert np.abs(host(fused) - ref).max() <= 2 * ULP
+
+
+@pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("g", [0.95, 1.05, 0.6, 1.5])
 def test_gamma(ops, dev, images, name, g):
     im = images[name]

@@ -63,7 +63,7 @@ def main():
         it_mean = float(res.tv_iterations.mean())
         # algorithmic bytes per pixel and call of every operator
         alg = {"mdimg_normalize_u16": 8, "mdimg_metrics": 4, "mdimg_fullref": 8, "mdimg_wavelet_denoise": 12,
-               "mdimg_light_denoise": 16, "mdimg_clahe": 16, "mdimg_gamma": 8, "mdimg_unsharp": 8,
+               "mdimg_light_denoise": 16, "mdimg_clahe": 16, "mdimg_clahe_gamma": 16, "mdimg_gamma": 8, "mdimg_unsharp": 8,
                "mdimg_bilateral": 8, "mdimg_tv_chambolle": 20 * it_mean + 4, "mdimg_clip01": 8,
                "mdimg_estimate_sigma": 4, "mdimg_quality": 4}
         peak = 6552.6

@@ -86,7 +86,7 @@ __device__ __forceinline__ void hist_add(unsigned* h, int bin, bool valid, int l
     }
 }
 
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
 k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
                 float* __restrict__ gout, unsigned* __restrict__ l1x, unsigned* __restrict__ l1g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -121,7 +121,7 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
         box_horizontal_f<7, 2>(vin, inv7, [&](int r, int c, const float (&m)[2]) {
             if (y0 + r < d.h && x0 + c < d.w) {
                 const float lv = fmaxf(__fsub_rn(m[1], __fmul_rn(m[0], m[0])), 0.0f);
-                const double ls = (double)__fsqrt_rn(lv);
+                const double ls = (double)sqrt_rn_fast(lv);
                 ls1 += ls;
                 ls2 += ls * ls;
             }
@@ -158,7 +158,7 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
             const float lap = (float)(4.0 * m1 - u1 - m0 - m2 - n1);
             const float sh = (float)(0.25 * (u0 - n0) + 0.5 * (u1 - n1) + 0.25 * (u2 - n2));
             const float sv = (float)(0.25 * (u0 - u2) + 0.5 * (m0 - m2) + 0.25 * (n0 - n2));
-            const float g = __fsqrt_rn(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
+            const float g = sqrt_rn_fast(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
             int b256 = (int)(xc * 256.0f);
             b256 = b256 > 255 ? 255 : b256;
             if (valid) {
@@ -252,7 +252,7 @@ k_edge_stats(const float* __restrict__ img, Dims d, double* __restrict__ acc2) {
                 const float lap = (float)(4.0 * xc - n01 - n10 - n12 - n21);
                 const float sh = (float)(0.25 * (n00 - n20) + 0.5 * (n01 - n21) + 0.25 * (n02 - n22));
                 const float sv = (float)(0.25 * (n00 - n02) + 0.5 * (n10 - n12) + 0.25 * (n20 - n22));
-                const float g = __fsqrt_rn(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
+                const float g = sqrt_rn_fast(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
                 v[0] += (double)fabsf(lap);
                 v[1] += (double)g;
             }

@@ -17,6 +17,7 @@
 // float32-store per tap.  Measured difference to the oracle: a few float32 ulps (tests allow 16).
 #include "enhance.cuh"
 #include "boxfilter.cuh"
+#include "packed.cuh"
 
 namespace mdimg {
 
@@ -28,13 +29,16 @@ constexpr int MAXD = 9;
 
 struct SpatialW { float w[MAXD * MAXD]; };
 
+// Two adjacent pixels per thread on the packed float32x2 pipe (FADD2 / FMUL2 / FFMA2): per tap and
+// pixel pair 6 packed instructions + 2 MUFU.EX2, and the d + 1 neighbours of a row are loaded once
+// for both pixels (64-bit shared loads).  The per-pixel operations and their order are unchanged.
 template <int R>
 __global__ void __launch_bounds__(NT)
 k_bilateral(const float* __restrict__ in, float* __restrict__ out, Dims d, const SpatialW sw,
             float neg_k) {
     constexpr int D = 2 * R + 1;
-    constexpr int XW = TW + 2 * R, XH = TH + 2 * R, XP = XW + 1;
-    __shared__ float X[XH][XP];
+    constexpr int XW = TW + 2 * R, XH = TH + 2 * R, XP = XW;      // even pitch: pixel pairs stay 8-byte aligned
+    __shared__ __align__(8) float X[XH][XP];
     const int s = slice_of(d.sel, blockIdx.y);
     const int tiles_x = (d.w + TW - 1) / TW;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -44,30 +48,51 @@ k_bilateral(const float* __restrict__ in, float* __restrict__ out, Dims d, const
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     load_tile<XW, XH, R, 1>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) { X[r][c] = v; });
     __syncthreads();
+    const int c = 2 * lane;                                       // this thread's pair: columns c, c + 1
+    const int gx = x0 + c;
+    const float2 k2 = bc2(neg_k);
 #pragma unroll
-    for (int j2 = 0; j2 < TH / 8; ++j2)
+    for (int j2 = 0; j2 < TH / 8; ++j2) {
+        const int r = wid + 8 * j2;
+        const int gy = y0 + r;
+        if (gy < d.h && gx < d.w) {
+            const float2 xc = *reinterpret_cast<const float2*>(&X[r + R][c + R - (R & 1)]);
+            const float2 ctr = (R & 1) ? make_float2(xc.y, X[r + R][c + R + 1]) : xc;
+            float2 res = make_float2(0.0f, 0.0f), wsum = make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int i2 = 0; i2 < TW / 32; ++i2) {
-            const int r = wid + 8 * j2, c = lane + 32 * i2;
-            const int gy = y0 + r, gx = x0 + c;
-            if (gy < d.h && gx < d.w) {
-                const float xc = X[r + R][c + R];
-                float res = 0.0f, wsum = 0.0f;
+            for (int dy = 0; dy < D; ++dy) {
+                float v[D + 1];
 #pragma unroll
-                for (int dy = 0; dy < D; ++dy)
+                for (int q = 0; q < (D + 1) / 2; ++q) {
+                    const float2 t = *reinterpret_cast<const float2*>(&X[r + dy][c + 2 * q]);
+                    v[2 * q] = t.x;
+                    v[2 * q + 1] = t.y;
+                }
 #pragma unroll
-                    for (int dx = 0; dx < D; ++dx) {
-                        const float nb = X[r + dy][c + dx];
-                        const float diff = xc - nb;
-                        // exp(-diff^2 / (2 sc^2)) = 2^(diff^2 * neg_k), neg_k = -log2(e) / (2 sc^2)
-                        const float iw = exp2f(diff * diff * neg_k);
-                        const float w = sw.w[dy * D + dx] * iw;
-                        res = fmaf(w, nb, res);
-                        wsum += w;
-                    }
-                dst[(size_t)gy * d.w + gx] = __fdiv_rn(res, __fadd_rn(wsum, 1e-10f));
+                for (int dx = 0; dx < D; ++dx) {
+                    const float2 nb = make_float2(v[dx], v[dx + 1]);
+                    const float2 diff = sub2(ctr, nb);
+                    // exp(-diff^2 / (2 sc^2)) = 2^(diff^2 * neg_k), neg_k = -log2(e) / (2 sc^2)
+                    const float2 e = mul2(mul2(diff, diff), k2);
+                    float2 iw;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(iw.x) : "f"(e.x));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(iw.y) : "f"(e.y));
+                    const float2 w = mul2(bc2(sw.w[dy * D + dx]), iw);
+                    res = fma2(w, nb, res);
+                    wsum = add2(wsum, w);
+                }
+            }
+            const float o0 = __fdiv_rn(res.x, __fadd_rn(wsum.x, 1e-10f));
+            const float o1 = __fdiv_rn(res.y, __fadd_rn(wsum.y, 1e-10f));
+            float* o = dst + (size_t)gy * d.w + gx;
+            if (gx + 1 < d.w && ((d.w & 1) == 0)) {
+                *reinterpret_cast<float2*>(o) = make_float2(o0, o1);
+            } else {
+                o[0] = o0;
+                if (gx + 1 < d.w) o[1] = o1;
             }
         }
+    }
 }
 
 template <int R>

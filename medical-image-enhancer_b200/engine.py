@@ -297,7 +297,13 @@ class Engine:
             if sel_ is not None:
                 ops.metrics(cur, with_niqe=True, sel=sel_, out=rows)
 
+        # A slice a guard modifies is measured again -- but only for what the NEXT guard looks at
+        # (estimate_sigma after the halo re-run, the NIQE approximation after that / the noise
+        # correction); its full compute_metrics row is produced once, after the last guard.
         rows_h = rows.cpu().numpy()
+        sig1 = rows_h[:, 0].copy()               # estimate_sigma(enhanced)
+        niqe1 = rows_h[:, MC_NIQE].copy()        # compute_niqe_approximation(enhanced)
+        dirty = np.zeros(n, bool)                # modified since `rows` was computed
         halo = np.zeros(n, bool)
         if "unsharp" in plan_ops:   # _check_halo -> re-run in the plan's own order with amount / 2
             halo = rows_h[:, MC_EDGE_RATIO] > 1.5
@@ -317,12 +323,12 @@ class Engine:
                     labels[i].append(f"[safeguard] Unsharp reduced to {reduced:.2f}")
                 if st2["tv_iters"] is not None and tv_iters is not None:
                     tv_iters = torch.where(torch.from_numpy(halo).to(ops.device), st2["tv_iters"], tv_iters)
-                remeasure(halo)
-                rows_h = rows.cpu().numpy()
+                dirty |= halo
+                sig1[halo] = ops.estimate_sigma(cur, sel=sel).cpu().numpy()[halo]
 
         # _check_noise_amplification -> corrective light denoise (enhancement.py:55-63,356-360)
         with np.errstate(invalid="ignore"):
-            noise = (~(s0h < 1e-8)) & (rows_h[:, 0] > s0h * 1.3)
+            noise = (~(s0h < 1e-8)) & (sig1 > s0h * 1.3)
         sel = self._sel_tensor(noise)
         if sel is not None:
             logger.warning(NOISE_MSG)
@@ -330,19 +336,22 @@ class Engine:
             ops.clip01(cur, cur, sel=sel)
             for i in np.flatnonzero(noise):
                 labels[i].append("Auto-corrective denoise (noise guard)")
-            remeasure(noise)
-            rows_h = rows.cpu().numpy()
+            dirty |= noise
 
         # _check_over_processing: NIQE-approx degradation > 0.5 -> 0.6*enhanced + 0.4*original
+        sel = self._sel_tensor(dirty)
+        if sel is not None:
+            niqe1[dirty] = ops.quality(cur, niqe=True, sel=sel)[:, 1].cpu().numpy()[dirty]
         with np.errstate(invalid="ignore"):
-            over = (rows_h[:, MC_NIQE] - nb) > 0.5
+            over = (niqe1 - nb) > 0.5
         sel = self._sel_tensor(over)
         if sel is not None:
             logger.warning(OVER_MSG)
             ops.axpby(cur, image, cur, 0.6, 0.4, clip01=True, sel=sel)
             for i in np.flatnonzero(over):
                 labels[i].append("Blend-back 40% original (over-processing guard)")
-            remeasure(over)
+            dirty |= over
+        remeasure(dirty)
 
         errors = state.get("errors", {})
         if errors:

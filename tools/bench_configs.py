@@ -55,6 +55,31 @@ def main():
     out["C3"] = {"images": n3, "size": 3000, "ms": ms, "mpx_per_s": px / ms / 1e3, "images_per_s": n3 / ms * 1e3,
                  "algorithmic_GBps": 72 * px / ms / 1e6, "frac_of_hbm_peak": 72 * px / ms / 1e6 / PEAK,
                  "note": f"{len(base)} distinct images repeated to {n3}; chunk 16 images"}
+    # per-operator device time of one C3 pass (CUDA events around every C-ABI call)
+    from collections import defaultdict
+    from mdimg_b200.stack import StackOps
+    events = []
+    orig_call = StackOps._call
+
+    def timed_call(self, fn, *args):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig_call(self, fn, *args)
+        b.record()
+        events.append((fn.__name__, a, b))
+
+    StackOps._call = timed_call
+    res3 = process_stack(dev, plan, chunk=16, ops=ops, workers=1)
+    torch.cuda.synchronize()
+    StackOps._call = orig_call
+    agg, cnt = defaultdict(float), defaultdict(int)
+    for name, a, b in events:
+        agg[name] += a.elapsed_time(b)
+        cnt[name] += 1
+    out["C3"]["ops_ms"] = {k: round(v, 2) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
+    out["C3"]["ops_calls"] = dict(cnt)
+    out["C3"]["guards"] = {"halo": int(res3.packed[:, 50].sum()), "noise": int(res3.packed[:, 51].sum()),
+                           "over": int(res3.packed[:, 52].sum())}
     del dev
     torch.cuda.empty_cache()
 

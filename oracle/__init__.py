@@ -25,4 +25,9 @@ PARITY STATUS
   orthogonality, hand-computed answers), cv2 cross-checks and the reference's own
   property tests, not against outputs of a real skimage/pywt install.
 * numpy semantics follow numpy >= 2 (NEP 50 promotion), which is what is installed.
+
+* The control flow above those leaves (``ref_metrics.py``, ``ref_enhancement.py``) IS pinned:
+  ``tests/golden/make_reference_glue.py`` executes the reference's own modules with a stand-in
+  ``skimage`` whose leaves are this package's restatements, and ``tests/test_oracle.py`` requires
+  the restated control flow to reproduce those outputs bit for bit.
 """

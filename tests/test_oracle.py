@@ -224,3 +224,86 @@ def test_numpy_scipy_known_answers():
     assert np.pad(np.arange(4), 2, mode="reflect").tolist() == [2, 1, 0, 1, 2, 3, 2, 1]
     assert np.pad(np.arange(4), 2, mode="symmetric").tolist() == [1, 0, 0, 1, 2, 3, 3, 2]
     assert float(np.percentile(np.arange(11, dtype=np.float32), 25)) == 2.5
+
+
+# ----------------------------------------------------------------------------------------------
+# The restated control flow against the reference's OWN SOURCE (tests/golden/make_reference_glue.py:
+# the reference's pipeline/metrics.py and pipeline/enhancement.py executed with the skimage leaves
+# replaced by the oracle's leaf restatements).  Everything above the leaves must agree exactly.
+# ----------------------------------------------------------------------------------------------
+def _glue():
+    return (json.loads((GOLDEN / "reference_glue.json").read_text()), np.load(GOLDEN / "reference_glue.npz"))
+
+
+def _glue_images(synth):
+    ims = {"clean64": synth.fixture_clean(), "noisy64": synth.fixture_noisy(), "lowc64": synth.fixture_low_contrast()}
+    ims["ct96"] = omet.normalize_image(synth.ct_slice(1000, 0.25, size=96))
+    return ims
+
+
+def _plan_from_json(defn):
+    from mdimg_b200.pipeline.schemas import EnhancementParams, EnhancementPlan
+    return EnhancementPlan(recommended_ops=defn["recommended_ops"], params=EnhancementParams(**defn["params"]))
+
+
+def _same(a, b):
+    if isinstance(a, float) and isinstance(b, float):
+        return a == b or (np.isnan(a) and np.isnan(b))
+    return a == b
+
+
+GLUE_IMAGES = ["clean64", "noisy64", "lowc64", "ct96"]
+
+
+@pytest.mark.parametrize("name", GLUE_IMAGES)
+def test_restated_metrics_equal_reference_source(synth, name):
+    g, _ = _glue()
+    im = _glue_images(synth)[name]
+    m = omet.compute_metrics(im)
+    assert list(m) == list(g["metrics"][name])                   # same 16 keys, same order
+    for k, v in g["metrics"][name].items():
+        assert m[k] == v, (k, m[k], v)                           # bit for bit
+    assert omet.detect_issues(m) == g["issues"][name]
+    assert omet.compute_niqe_approximation(im) == g["niqe"][name]
+    assert omet.compute_edge_ratio(im) == g["edge_ratio"][name]
+
+
+@pytest.mark.parametrize("name", GLUE_IMAGES)
+def test_restated_issue_driven_enhancement_equals_reference_source(synth, name):
+    g, arrs = _glue()
+    im = _glue_images(synth)[name]
+    keys = [k for k in g["from_issues"] if k.startswith(name + "|")]
+    assert len(keys) >= 4
+    for key in keys:
+        issues = [s for s in key.split("|", 1)[1].split(",") if s]
+        out, labels = oenh.apply_enhancements(im, issues)
+        assert labels == g["from_issues"][key], key
+        np.testing.assert_array_equal(out, arrs[f"issues|{key}"], err_msg=key)
+
+
+@pytest.mark.parametrize("name", GLUE_IMAGES)
+def test_restated_plan_enhancement_validation_and_score_equal_reference_source(synth, name):
+    g, arrs = _glue()
+    im = _glue_images(synth)[name]
+    for pname, defn in g["plan_defs"].items():
+        key = f"{name}|{pname}"
+        plan = _plan_from_json(defn)
+        want = g["plans"][key]
+        if isinstance(want, dict):                                # the reference raised
+            with pytest.raises(ValueError) as ei:
+                oenh.apply_enhancements_from_params(im, plan)
+            assert f"ValueError: {ei.value}" == want["error"]
+            continue
+        out, labels = oenh.apply_enhancements_from_params(im, plan)
+        assert labels == want, key
+        np.testing.assert_array_equal(out, arrs[f"plan|{key}"], err_msg=key)
+        val = omet.compute_validation(im, out)
+        gv = g["validation"][key]
+        assert list(val) == list(gv), key                          # 38 entries, same order
+        for k, v in gv.items():
+            if isinstance(v, dict):
+                assert val[k] == v, (key, k)
+            else:
+                assert _same(val[k], v), (key, k, val[k], v)
+        score, breakdown = omet.compute_objective_score(val)
+        assert score == g["score"][key]["score"] and breakdown == g["score"][key]["breakdown"], key

@@ -147,55 +147,95 @@ k_sel_scan1(Params P, Dims d) {
     }
 }
 
-// Per-element work of a refinement pass: level-1 bin -> one byte lookup; only elements of a bin
-// that holds an unresolved query (about 1 %) go on to the range tests and the histogram.
+// Per-element work of a refinement pass: level-1 bin -> one byte lookup (12 instructions, branch
+// free).  Only ~1 % of the elements fall into a bin that holds an unresolved query, but a warp sees
+// at least one of them almost every other step, and running the range search + histogram update
+// divergently for a single lane would cost more than the whole fast path.  Hits are therefore
+// compacted into a per-warp queue (ballot + popc) and drained 32 at a time with all lanes busy.
+constexpr int WQ = 64;                             // queue slots per warp: < 32 pending + one full ballot
+
+struct RefineCtx {
+    unsigned flag_sa;                              // shared-window address of the bin flag table
+    unsigned* q;                                   // this warp's queue (shared memory)
+    int qn;                                        // queued keys (warp-uniform)
+    int nu;
+    const unsigned* ulo; const unsigned* uspan; const int* ushift;
+    unsigned* hbase;
+    int lane;
+};
+
+__device__ __forceinline__ void refine_account(const RefineCtx& c, unsigned key, unsigned mask) {
+    for (int j = 0; j < c.nu; ++j) {
+        const unsigned off = key - c.ulo[j];
+        if (off <= c.uspan[j]) {
+            const unsigned slot = (unsigned)j * SEL_REFINE_BINS + (off >> c.ushift[j]);
+            const unsigned peers = __match_any_sync(__activemask(), slot);
+            if (c.lane == __ffs(peers) - 1) atomicAdd(c.hbase + slot, (unsigned)__popc(peers));
+            break;
+        }
+    }
+    (void)mask;
+}
+
+__device__ __forceinline__ void refine_drain32(RefineCtx& c) {
+    __syncwarp();
+    refine_account(c, c.q[c.lane], 0xffffffffu);
+    const int rest = c.qn - 32;
+    __syncwarp();
+    const unsigned t = c.lane < rest ? c.q[32 + c.lane] : 0u;
+    __syncwarp();
+    if (c.lane < rest) c.q[c.lane] = t;
+    c.qn = rest;
+}
+
+// All 32 lanes call (valid = this lane holds an element).
 template <bool ABS>
-__device__ __forceinline__ void refine_visit(float f, unsigned flag_sa, int nu,
-                                             const unsigned* __restrict__ ulo, const unsigned* __restrict__ uspan,
-                                             const int* __restrict__ ushift, unsigned* __restrict__ hbase, int lane) {
+__device__ __forceinline__ void refine_visit(RefineCtx& c, float f, bool valid) {
     f = __fadd_rn(ABS ? fabsf(f) : f, 0.0f);
     unsigned hit;      // shared-window address kept in a register: ptxas otherwise rebuilds it per element
-    asm("ld.shared.u8 %0, [%1];" : "=r"(hit) : "r"(flag_sa + (unsigned)sel_bin1(f)));
-    if (hit) {
-        const unsigned key = f2key(f);
-        for (int j = 0; j < nu; ++j) {
-            const unsigned off = key - ulo[j];
-            if (off <= uspan[j]) {
-                const unsigned slot = (unsigned)j * SEL_REFINE_BINS + (off >> ushift[j]);
-                const unsigned peers = __match_any_sync(__activemask(), slot);
-                if (lane == __ffs(peers) - 1) atomicAdd(hbase + slot, (unsigned)__popc(peers));
-                break;
-            }
-        }
+    asm("ld.shared.u8 %0, [%1];" : "=r"(hit) : "r"(c.flag_sa + (unsigned)sel_bin1(f)));
+    const unsigned m = __ballot_sync(0xffffffffu, valid && hit);
+    if (m) {                                       // warp-uniform
+        if (valid && hit) c.q[c.qn + __popc(m & ((1u << c.lane) - 1u))] = f2key(f);
+        c.qn += __popc(m);
+        if (c.qn >= 32) refine_drain32(c);
     }
 }
 
 template <bool ABS>
-__device__ __forceinline__ void refine_stream(const float* __restrict__ v, int len, int tid, int nthr,
-                                              unsigned flag_sa, int nu,
-                                              const unsigned* __restrict__ ulo, const unsigned* __restrict__ uspan,
-                                              const int* __restrict__ ushift, unsigned* __restrict__ hbase, int lane) {
-#define MDIMG_VISIT(x) refine_visit<ABS>(x, flag_sa, nu, ulo, uspan, ushift, hbase, lane)
+__device__ __forceinline__ void refine_stream(RefineCtx& c, const float* __restrict__ v, int len, int tid, int nthr) {
+    const int lane = c.lane;
     if ((((uintptr_t)v) & 15) == 0) {
         const int n4 = len >> 2;
         const float4* v4 = reinterpret_cast<const float4*>(v);
         int i = tid;
-        for (; i + 3 * nthr < n4; i += 4 * nthr) {                 // four independent 128-bit loads in flight
-            const float4 a = v4[i], b = v4[i + nthr], c = v4[i + 2 * nthr], e = v4[i + 3 * nthr];
-            MDIMG_VISIT(a.x); MDIMG_VISIT(a.y); MDIMG_VISIT(a.z); MDIMG_VISIT(a.w);
-            MDIMG_VISIT(b.x); MDIMG_VISIT(b.y); MDIMG_VISIT(b.z); MDIMG_VISIT(b.w);
-            MDIMG_VISIT(c.x); MDIMG_VISIT(c.y); MDIMG_VISIT(c.z); MDIMG_VISIT(c.w);
-            MDIMG_VISIT(e.x); MDIMG_VISIT(e.y); MDIMG_VISIT(e.z); MDIMG_VISIT(e.w);
+        // four independent 128-bit loads in flight while the whole warp is in range (warp-uniform test)
+        for (; i - lane + 31 + 3 * nthr < n4; i += 4 * nthr) {
+            const float4 a = v4[i], b = v4[i + nthr], d = v4[i + 2 * nthr], e = v4[i + 3 * nthr];
+            refine_visit<ABS>(c, a.x, true); refine_visit<ABS>(c, a.y, true); refine_visit<ABS>(c, a.z, true); refine_visit<ABS>(c, a.w, true);
+            refine_visit<ABS>(c, b.x, true); refine_visit<ABS>(c, b.y, true); refine_visit<ABS>(c, b.z, true); refine_visit<ABS>(c, b.w, true);
+            refine_visit<ABS>(c, d.x, true); refine_visit<ABS>(c, d.y, true); refine_visit<ABS>(c, d.z, true); refine_visit<ABS>(c, d.w, true);
+            refine_visit<ABS>(c, e.x, true); refine_visit<ABS>(c, e.y, true); refine_visit<ABS>(c, e.z, true); refine_visit<ABS>(c, e.w, true);
         }
-        for (; i < n4; i += nthr) {
-            const float4 q = v4[i];
-            MDIMG_VISIT(q.x); MDIMG_VISIT(q.y); MDIMG_VISIT(q.z); MDIMG_VISIT(q.w);
+        for (; i - lane < n4; i += nthr) {
+            const bool ok = i < n4;
+            const float4 q = ok ? v4[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            refine_visit<ABS>(c, q.x, ok); refine_visit<ABS>(c, q.y, ok); refine_visit<ABS>(c, q.z, ok); refine_visit<ABS>(c, q.w, ok);
         }
-        for (int k = (n4 << 2) + tid; k < len; k += nthr) MDIMG_VISIT(v[k]);
+        for (int k = (n4 << 2) + tid; k - lane < len; k += nthr) {
+            const bool ok = k < len;
+            refine_visit<ABS>(c, ok ? v[k] : 0.0f, ok);
+        }
     } else {
-        for (int i = tid; i < len; i += nthr) MDIMG_VISIT(v[i]);
+        for (int i = tid; i - lane < len; i += nthr) {
+            const bool ok = i < len;
+            refine_visit<ABS>(c, ok ? v[i] : 0.0f, ok);
+        }
     }
-#undef MDIMG_VISIT
+    __syncwarp();
+    if (lane < c.qn) refine_account(c, c.q[lane], 0u);            // leftovers
+    __syncwarp();
+    c.qn = 0;
 }
 
 // One refinement pass (+ the slice's scan, done by the last block to finish).
@@ -207,6 +247,7 @@ k_sel_refine(Params P, Dims d) {
     __shared__ int nu_s, last_s;
     __shared__ unsigned cum[SEL_REFINE_BINS];
     __shared__ unsigned warp_tot[ST / 32];
+    __shared__ unsigned queue[ST / 32][WQ];
     __shared__ SelState st;
     const JobDev& J = P.job[blockIdx.z];
     const int si = blockIdx.y;
@@ -229,10 +270,14 @@ k_sel_refine(Params P, Dims d) {
     unsigned* hbase = J.hist + (size_t)si * SEL_MAX_Q * SEL_REFINE_BINS;
     const int lane = threadIdx.x & 31;
     const int tid = blockIdx.x * ST + threadIdx.x, nthr = gridDim.x * ST;
-    unsigned flag_sa;   // opaque copy: ptxas would otherwise rematerialise the window base per element
-    asm volatile("mov.u32 %0, %1;" : "=r"(flag_sa) : "r"((unsigned)__cvta_generic_to_shared(flag)));
-    if (J.opts & SEL_ABS) refine_stream<true>(v, J.len, tid, nthr, flag_sa, nu, ulo, uspan, ushift, hbase, lane);
-    else refine_stream<false>(v, J.len, tid, nthr, flag_sa, nu, ulo, uspan, ushift, hbase, lane);
+    RefineCtx c;
+    // opaque copy: ptxas would otherwise rematerialise the shared window base per element
+    asm volatile("mov.u32 %0, %1;" : "=r"(c.flag_sa) : "r"((unsigned)__cvta_generic_to_shared(flag)));
+    c.q = queue[threadIdx.x >> 5];
+    c.qn = 0;
+    c.nu = nu; c.ulo = ulo; c.uspan = uspan; c.ushift = ushift; c.hbase = hbase; c.lane = lane;
+    if (J.opts & SEL_ABS) refine_stream<true>(c, v, J.len, tid, nthr);
+    else refine_stream<false>(c, v, J.len, tid, nthr);
 
     // ---- last block of this slice: scan the digit histograms, narrow the ranges ----
     __threadfence();

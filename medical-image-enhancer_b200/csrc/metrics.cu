@@ -397,19 +397,29 @@ k_grad_pass(const float* __restrict__ gbuf, Dims d, const GradPrep* __restrict__
     const int len = d.h * d.w;
     unsigned c_edge = 0, c_strong = 0;
     double s_strong[1] = {0.0};
-    for (int i = blockIdx.x * NT + tid; i < len; i += gridDim.x * NT) {
-        const float v = g[i];
-        c_edge += (v > thr);
-        if (v >= t90) { c_strong++; s_strong[0] += (double)v; }
-        if (v >= 0.0f && v <= last) {
-            int b = (int)__fmul_rn(__fdiv_rn(v, denom), 128.0f);
-            if (b == 128) b = 127;
-            if (v < edges[b]) b -= 1;
-            if (b != 127 && v >= edges[b + 1]) b += 1;
-            unsigned am = __activemask();
-            unsigned peers = __match_any_sync(am, b);
-            if (lane == __ffs(peers) - 1) atomicAdd(&h[b], (unsigned)__popc(peers));
+    auto visit = [&](float v, bool ok) {
+        c_edge += (ok && v > thr);
+        if (ok && v >= t90) { c_strong++; s_strong[0] += (double)v; }
+        const bool in = ok && v >= 0.0f && v <= last;
+        int b = (int)__fmul_rn(__fdiv_rn(v, denom), 128.0f);
+        b = min(max(b, 0), 127);
+        if (v < edges[b]) b -= 1;                 // numpy corrects the tentative bin against the edge array
+        else if (b != 127 && v >= edges[b + 1]) b += 1;
+        b = min(max(b, 0), 127);
+        hist_add(h, b, in, lane);                 // warp-uniform fast path for flat regions
+    };
+    const int tid0 = blockIdx.x * NT + tid, nthr = gridDim.x * NT;
+    if ((((uintptr_t)g) & 15) == 0) {
+        const int n4 = len >> 2;
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        for (int i = tid0; i - lane < n4; i += nthr) {        // warp-uniform trip count (hist_add votes)
+            const bool ok = i < n4;
+            const float4 q = ok ? g4[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            visit(q.x, ok); visit(q.y, ok); visit(q.z, ok); visit(q.w, ok);
         }
+        for (int i = (n4 << 2) + tid0; i - lane < len; i += nthr) visit(i < len ? g[i] : 0.0f, i < len);
+    } else {
+        for (int i = tid0; i - lane < len; i += nthr) visit(i < len ? g[i] : 0.0f, i < len);
     }
     __syncthreads();
     block_sum<1>(s_strong, red);

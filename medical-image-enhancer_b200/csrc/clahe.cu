@@ -59,17 +59,41 @@ __global__ void k_clahe_prep(Dims d, const uint2* __restrict__ mm, SliceRange* _
     rng[si] = r;
 }
 
-__device__ __forceinline__ unsigned quantise(float x, unsigned umin, unsigned umax) {
-    unsigned u = to_u16(x);
+// rescale of the uint16 image to 14 bits (float64, round half to even), skimage _clahe step (ii)
+__device__ __forceinline__ unsigned quantise_u16(unsigned u, unsigned umin, unsigned umax) {
     if (umin == umax) return u > 16383u ? 16383u : u;
     double t = __ddiv_rn((double)(int)(u - umin), (double)(int)(umax - umin));
     t = __dadd_rn(__dmul_rn(t, 16383.0), 0.0);
     return (unsigned)rint(t);
 }
 
+// The float64 quantisation depends only on the 16-bit level: one table entry per level and slice
+// (gray bin = quantised level / 65) instead of a float64 division per pixel.
+constexpr int NU16 = 65536;
+
+__global__ void __launch_bounds__(NT)
+k_clahe_binlut(Dims d, const SliceRange* __restrict__ rng, const int* __restrict__ status,
+               uint8_t* __restrict__ lut) {
+    const int si = blockIdx.y;
+    if (status[slice_of(d.sel, si)]) return;
+    const unsigned u = blockIdx.x * NT + threadIdx.x;
+    const unsigned umin = rng[si].umin, umax = rng[si].umax;
+    unsigned b = 0;
+    if (u >= umin && u <= umax) b = quantise_u16(u, umin, umax) / 65u;
+    lut[(size_t)si * NU16 + u] = (uint8_t)b;
+}
+
+// np.pad 'reflect' (whole-sample mirror) for an index that overshoots by less than the extent;
+// falls back to the general form otherwise (tiny images).
+__device__ __forceinline__ int mirror_fast(int i, int n) {
+    int r = i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i);
+    if (r < 0 || r >= n) r = refl_mirror(i, n);
+    return r;
+}
+
 // One warp per contextual region.
 __global__ void __launch_bounds__(NT)
-k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const SliceRange* __restrict__ rng,
+k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* __restrict__ binlut,
              const int* __restrict__ status, uint8_t* __restrict__ bins, uint16_t* __restrict__ maps) {
     __shared__ int hist[WARPS][NBINS];
     const int si = blockIdx.y;
@@ -80,21 +104,24 @@ k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const SliceRange
     if (tile >= g.nty * g.ntx) return;
     const int ty = tile / g.ntx, tx = tile - ty * g.ntx;
     const int k = g.k;
-    const unsigned umin = rng[si].umin, umax = rng[si].umax;
     int* h = hist[wid];
     for (int i = lane; i < NBINS; i += 32) h[i] = 0;
     __syncwarp();
     const float* src = in + (size_t)s * d.h * d.w;
     uint8_t* bdst = bins + (size_t)si * d.h * d.w;
+    const uint8_t* lut = binlut + (size_t)si * NU16;
     const int kk = k * k;
+    // lane -> (row, column) inside the region, advanced by 32 elements per trip without divisions
+    int ry = lane / k, rx = lane - ry * k;
+    const int dry = 32 / k, drx = 32 - dry * k;
     for (int i = lane; i < kk; i += 32) {
-        const int ry = i / k, rx = i - ry * k;
         const int oy = ty * k + ry, ox = tx * k + rx;        // padded index minus pad_start
-        const int gy = refl_mirror(oy, d.h), gx = refl_mirror(ox, d.w);
-        const unsigned q = quantise(src[(size_t)gy * d.w + gx], umin, umax);
-        const int b = (int)(q / 65u);
+        const int gy = mirror_fast(oy, d.h), gx = mirror_fast(ox, d.w);
+        const int b = lut[to_u16(src[(size_t)gy * d.w + gx])];
         atomicAdd(&h[b], 1);
         if (oy < d.h && ox < d.w) bdst[(size_t)oy * d.w + ox] = (uint8_t)b;
+        rx += drx; ry += dry;
+        if (rx >= k) { rx -= k; ry += 1; }
     }
     __syncwarp();
 
@@ -191,8 +218,11 @@ k_clahe_blend(Dims d, ClaheGeom g, SliceRange* __restrict__ rng, const int* __re
         const size_t o = (size_t)y * d.w + x;
         const int b = bins[(size_t)si * d.h * d.w + o];
         const int py = y + k / 2, px = x + k / 2;
-        const int byk = py / k, iy = py - byk * k;
-        const int bxk = px / k, ix = px - bxk * k;
+        // floor(p / k) for k <= 48, p < 2^20: the fractional part of p / k is a multiple of 1 / k,
+        // far from the float32 rounding error of (p + 0.5) * (1 / k)
+        const float rk = __frcp_rn((float)k);
+        const int byk = (int)(((float)py + 0.5f) * rk), iy = py - byk * k;
+        const int bxk = (int)(((float)px + 0.5f) * rk), ix = px - bxk * k;
         // map_array is the LUT grid edge-padded by one: entry j -> region clamp(j - 1)
         const int t0y = min(max(byk - 1, 0), g.nty - 1), t1y = min(byk, g.nty - 1);
         const int t0x = min(max(bxk - 1, 0), g.ntx - 1), t1x = min(bxk, g.ntx - 1);
@@ -275,7 +305,7 @@ k_clahe_final(Dims d, const int* __restrict__ status, const uint16_t* __restrict
     }
 }
 
-struct ClaheBufs { SliceRange* rng; uint8_t* bins; uint16_t* maps; uint16_t* v; float* lut; };
+struct ClaheBufs { SliceRange* rng; uint8_t* bins; uint16_t* maps; uint16_t* v; float* lut; uint8_t* binlut; };
 
 void carve(Arena& a, int n_sel, int h, int w, int nty, int ntx, ClaheBufs& b) {
     b.rng = a.take<SliceRange>(n_sel);
@@ -283,6 +313,7 @@ void carve(Arena& a, int n_sel, int h, int w, int nty, int ntx, ClaheBufs& b) {
     b.maps = a.take<uint16_t>((size_t)n_sel * nty * ntx * NBINS);
     b.v = a.take<uint16_t>((size_t)n_sel * h * w);
     b.lut = a.take<float>((size_t)n_sel * NLEVELS);
+    b.binlut = a.take<uint8_t>((size_t)n_sel * NU16);
 }
 
 inline void geom(int h, int w, int k, double clip_limit, ClaheGeom& g) {
@@ -327,7 +358,8 @@ int clahe_run(const float* in, float* out, const Dims& d, double clip_limit, int
     if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "clahe: workspace too small (%zu > %zu)", a.off, ws_bytes);
     MDIMG_LAUNCH k_clahe_prep<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, mm, b.rng, status);
     const int ntiles = g.nty * g.ntx;
-    MDIMG_LAUNCH k_clahe_hist<<<dim3((ntiles + WARPS - 1) / WARPS, d.n_sel), NT, 0, stream>>>(in, d, g, b.rng, status, b.bins, b.maps);
+    MDIMG_LAUNCH k_clahe_binlut<<<dim3(NU16 / NT, d.n_sel), NT, 0, stream>>>(d, b.rng, status, b.binlut);
+    MDIMG_LAUNCH k_clahe_hist<<<dim3((ntiles + WARPS - 1) / WARPS, d.n_sel), NT, 0, stream>>>(in, d, g, b.binlut, status, b.bins, b.maps);
     dim3 bgrid(((d.w + BW - 1) / BW) * ((d.h + BH - 1) / BH), d.n_sel);
     MDIMG_LAUNCH k_clahe_blend<<<bgrid, NT, 0, stream>>>(d, g, b.rng, status, b.bins, b.maps, b.v);
     long long len = d.px();

@@ -196,7 +196,13 @@ class Engine:
             else:
                 ops.copy(tmp, cur, sel=sel)
         elif name == "tv_denoise":
-            iters = ops.tv_chambolle(cur, cur, q.tv_weight, sel=sel)
+            # out of place: the result pass writes the image directly while neighbouring strips still
+            # read the input (an aliased output costs one more copy inside the library)
+            iters = ops.tv_chambolle(cur, tmp, q.tv_weight, sel=sel)
+            if sel is None:
+                cur, tmp = tmp, cur
+            else:
+                ops.copy(tmp, cur, sel=sel)
             state["tv_iters"] = iters
             state["nonneg"] = False
         return cur, tmp

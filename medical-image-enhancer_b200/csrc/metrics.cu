@@ -487,7 +487,7 @@ k_finalize(Dims d, const MetAcc* __restrict__ acc, const float* __restrict__ xse
     const float p25 = lerp_np(xs[2], xs[3], plan.gamma[1]);
     const float p75 = lerp_np(xs[4], xs[5], plan.gamma[2]);
     const float p95 = lerp_np(xs[6], xs[7], plan.gamma[3]);
-    const double sden = fmax(sigma, 1e-8);
+    const double sden = (1e-8 > sigma) ? 1e-8 : sigma;      // python max(sigma, 1e-8): a NaN sigma stays NaN
 
     o[MC_SIGMA] = sigma;
     o[MC_LAP_VAR] = f32r(lap_var);

@@ -58,6 +58,42 @@ def test_compute_metrics_rows(ops, dev, images, name):
     assert row[18] == pytest.approx(omet.compute_niqe_approximation(im), rel=1e-5)
 
 
+def _adversarial_images():
+    rng = np.random.default_rng(2024)
+    base = rng.random((96, 80), dtype=np.float32)
+    two = np.where(base > 0.5, np.float32(0.25), np.float32(0.75)).astype(np.float32)
+    quant = (np.round(base * 15) / 15).astype(np.float32)                 # 16 levels: huge ties
+    dark = (base * np.float32(1e-4)).astype(np.float32)                   # everything in the first bins
+    tiny = (base * np.float32(1e-30)).astype(np.float32)                  # below 2^-100 squared: denormal products
+    wide = ((base - 0.5) * 40).astype(np.float32)                         # negatives and values > 1
+    mostly_zero = np.where(base > 0.9, base, np.float32(0)).astype(np.float32)
+    cluster = (np.float32(0.02) + base * np.float32(2e-3)).astype(np.float32)   # dense narrow cluster (CT air after CLAHE)
+    ones = np.where(base > 0.3, np.float32(1.0), base).astype(np.float32)
+    ramp = np.linspace(0, 1, 96 * 80, dtype=np.float32).reshape(96, 80)
+    odd = rng.random((37, 53), dtype=np.float32)
+    return {"two_valued": two, "quantised": quant, "dark": dark, "tiny": tiny, "wide": wide,
+            "mostly_zero": mostly_zero, "cluster": cluster, "ones": ones, "ramp": ramp, "odd": odd,
+            "constant": np.full((64, 64), 0.375, np.float32), "zeros": np.zeros((64, 64), np.float32)}
+
+
+@pytest.mark.parametrize("name", sorted(_adversarial_images()))
+def test_order_statistics_on_adversarial_distributions(ops, dev, name):
+    """The range select behind every percentile / median (ties, dense clusters, negatives, values
+    above 1, zeros, tiny magnitudes, odd sizes): the percentile-based metrics equal numpy's exactly,
+    estimate_sigma (median of |db2 dd|) to the last bit, the others to 1e-5."""
+    im = _adversarial_images()[name]
+    row = ops.metrics(dev(im))[0].cpu().numpy()
+    ref = omet.compute_metrics(im)
+    got = dict(zip(omet.METRIC_KEYS, row[:16]))
+    # exact: numpy's float32 percentile arithmetic reproduced on exactly selected order statistics
+    p5, p25, p75, p95 = (np.percentile(im, q) for q in (5, 25, 75, 95))
+    assert got["histogram_spread"] == float(p75) - float(p25), name       # python-float difference, as the reference
+    assert row[21] == float(p5) and row[22] == float(p95), name           # MC_P05, MC_P95
+    assert got["sigma"] == ref["sigma"] or (np.isnan(got["sigma"]) and np.isnan(ref["sigma"])), name
+    for k, v in ref.items():
+        assert got[k] == pytest.approx(v, rel=1e-5, abs=1e-12, nan_ok=True), (name, k)
+
+
 @pytest.mark.parametrize("name", NAMES)
 def test_estimate_sigma_exact(ops, dev, images, name):
     im = images[name]

@@ -252,3 +252,89 @@ def test_score_plans_matches_the_tool_loop(ops, images, synth):
             ref_score, _ = omet.compute_objective_score(omet.compute_validation(images[name], ref_img))
             assert results[k].labels[i] == ref_labels
             assert scores[k, i] == pytest.approx(ref_score, abs=5e-4), (k, name)
+
+
+# ---- degenerate inputs: same result, same labels or the same exception as the reference flow ------
+def _degenerate_images():
+    rng = np.random.default_rng(99)
+    base = rng.random((48, 40), dtype=np.float32)
+    return {
+        "zeros": np.zeros((32, 32), np.float32),
+        "constant": np.full((40, 48), 0.5, np.float32),
+        "two_valued": np.where(base > 0.5, np.float32(0.2), np.float32(0.8)).astype(np.float32),
+        "tiny16": rng.random((16, 16), dtype=np.float32),
+        "odd": rng.random((37, 53), dtype=np.float32),
+        "one_hot": np.pad(np.ones((1, 1), np.float32), ((20, 19), (15, 24))),
+        "saturated": np.clip(base * 3 - 1, 0, 1).astype(np.float32),
+    }
+
+
+def _run_or_exc(fn):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            return fn(), None
+        except Exception as exc:  # noqa: BLE001
+            return None, exc
+
+
+@pytest.mark.parametrize("name", sorted(_degenerate_images()))
+@pytest.mark.parametrize("which", ["p_full", "p_cr", "issues_all"])
+def test_degenerate_inputs_follow_the_reference_flow(api, synth, name, which):
+    im = _degenerate_images()[name]
+    if which == "issues_all":
+        issues = ["noise", "blur", "low_contrast", "clipping_low"]
+        got, gexc = _run_or_exc(lambda: api.enhancement.apply_enhancements(im, issues))
+        ref, rexc = _run_or_exc(lambda: oenh.apply_enhancements(im, issues))
+    else:
+        plan = synth.plan_full() if which == "p_full" else synth.plan_cr()
+        got, gexc = _run_or_exc(lambda: api.enhancement.apply_enhancements_from_params(im, plan))
+        ref, rexc = _run_or_exc(lambda: oenh.apply_enhancements_from_params(im, plan))
+    if rexc is not None:
+        assert gexc is not None and type(gexc) is type(rexc), (name, which, rexc, gexc)
+        return
+    assert gexc is None, (name, which, gexc)
+    assert got[1] == ref[1], (name, which)                        # labels, safeguards included
+    a, b = got[0], ref[0]
+    assert a.shape == b.shape and a.dtype == np.float32
+    assert np.array_equal(np.isnan(a), np.isnan(b)), (name, which)
+    ok = ~np.isnan(b)
+    err = np.abs(a[ok].astype(np.float64) - b[ok])
+    assert err.size == 0 or float((err > LSB16).mean()) <= 0.01, (name, which, float(err.max()))
+
+
+@pytest.mark.parametrize("name", sorted(_degenerate_images()))
+def test_degenerate_inputs_metrics_and_validation(api, name):
+    im = _degenerate_images()[name]
+    # not an affine copy: the NIQE approximation and the edge ratio are scale invariant, which would
+    # leave `niqe_after <= niqe_before` to rounding noise
+    other = np.clip(np.sqrt(im) * np.float32(0.9) + np.float32(0.05) * im, 0, 1).astype(np.float32)
+    got, gexc = _run_or_exc(lambda: api.metrics.compute_validation(im, other))
+    ref, rexc = _run_or_exc(lambda: omet.compute_validation(im, other))
+    if rexc is not None:
+        assert gexc is not None and type(gexc) is type(rexc), (name, rexc, gexc)
+        return
+    assert gexc is None, (name, gexc)
+    assert list(got) == list(ref)
+    # A constant image is the one place where the 1e-5 relative tolerance cannot hold: numpy's float32
+    # pairwise mean of n equal values is not that value, so the reference reports std ~ 4e-9 (and
+    # lap_var ~ 1e-17) where the true value -- and ours -- is 0; gains divide that noise by 1e-8.
+    flat = float(np.ptp(im)) == 0.0 or float(np.ptp(other)) == 0.0
+    for k, v in ref.items():
+        if flat and (k.endswith(("_gain", "_change", "_before", "_after")) or k in ("quality_improvement", "meets_improvement", "passes", "metrics_before", "metrics_after", "niqe_improved")):
+            continue
+        if isinstance(v, dict):
+            for kk, vv in v.items():
+                assert got[k][kk] == pytest.approx(vv, rel=1e-5, abs=1e-9, nan_ok=True), (name, k, kk)
+        elif isinstance(v, bool):
+            # `niqe_after <= niqe_before` on (near-)ties is decided by rounding noise: the NIQE
+            # approximation is scale invariant, and any map between two-valued images is affine
+            tie = abs(ref["niqe_after"] - ref["niqe_before"]) <= 1e-5 * max(abs(ref["niqe_before"]), 1e-9)
+            if tie and k in ("niqe_improved", "passes"):
+                continue
+            assert got[k] is v, (name, k)
+        elif k.endswith(("_gain", "_change")) or k == "quality_improvement":
+            assert got[k] == pytest.approx(v, rel=2e-5, abs=2e-5, nan_ok=True), (name, k)
+        else:
+            assert got[k] == pytest.approx(v, rel=1e-5, abs=1e-9, nan_ok=True), (name, k)

@@ -81,6 +81,13 @@ size_t mdimg_workspace_bytes(int op, int n, int h, int w, int param);
 /* out_minmax: device float[n][2]. */
 int mdimg_minmax_f32(const float* img, int n, int h, int w, const int32_t* sel, int n_sel,
                      float* out_minmax, void* ws, size_t ws_bytes, void* stream);
+/* Report mosaic of save_visuals (pipeline/dicom_io.py:99-126: imshow(original, cmap="gray") next to
+ * imshow(enhanced, cmap="gray")): out = device uint8 [n][h][2w + gap], each panel autoscaled to its
+ * own min / max and quantised to matplotlib's 256 gray levels, `gap` columns of `gap_level` between
+ * them.  Workspace: MDIMG_OP_MINMAX twice (2 * n * 8 bytes). */
+int mdimg_mosaic_u8(const float* before, const float* after, uint8_t* out, int n, int h, int w,
+                    const int32_t* sel, int n_sel, int gap, int gap_level, void* ws, size_t ws_bytes,
+                    void* stream);
 /* normalize_image (pipeline/dicom_io.py:84-91): per-slice (x - min) / (max - min), zeros when
  * max - min < 1e-8. */
 int mdimg_normalize_u16(const uint16_t* in, float* out, int n, int h, int w, const int32_t* sel,

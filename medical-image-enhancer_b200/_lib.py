@@ -38,6 +38,7 @@ PROTOTYPES = {
     "mdimg_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
     "mdimg_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mdimg_minmax_f32": (_i, [_p, *_IMG, _p, *_WS]),
+    "mdimg_mosaic_u8": (_i, [_p, _p, _p, *_IMG, _i, _i, *_WS]),
     "mdimg_normalize_u16": (_i, [_p, _p, *_IMG, *_WS]),
     "mdimg_normalize_f32": (_i, [_p, _p, *_IMG, *_WS]),
     "mdimg_ingest_u16": (_i, [_p, _p, *_IMG, _d, _d, _i, _i, _i, *_WS]),

@@ -273,6 +273,25 @@ def _host_streams(device: torch.device, k: int):
     return _host_stream_cache[key]
 
 
+def save_stack_visuals(original: torch.Tensor, enhanced: torch.Tensor, out_dir: str, base_name: str,
+                       workers: int = 8, gap: int = 8) -> List[str]:
+    """Report mosaics for a whole stack (the reference writes one matplotlib figure
+    per image, pipeline/dicom_io.py:99-126): one launch quantises every before | after pair on the
+    GPU, the PNG encoding (zlib) runs on a host thread pool off the GPU's critical path.
+    Returns the file paths ``<out_dir>/<base_name>_<index>_before_after.png``."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    from . import png
+    ops = get_ops(original.device)
+    mosaics = ops.mosaic(original, enhanced, gap=gap).cpu().numpy()
+    os.makedirs(out_dir, exist_ok=True)
+    paths = [os.path.join(out_dir, f"{base_name}_{i:05d}_before_after.png") for i in range(mosaics.shape[0])]
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:      # zlib releases the GIL
+        list(pool.map(lambda t: png.write_gray8(t[0], t[1]), zip(paths, mosaics)))
+    return paths
+
+
 def score_plans(images: torch.Tensor, plans, ops: Optional[StackOps] = None):
     """Tuning-loop batch (reference: pipeline/tools.py:95-183 called once per
     candidate and image by the LLM tuner): evaluate K candidate plans on N normalised images.

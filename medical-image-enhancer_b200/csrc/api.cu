@@ -142,6 +142,22 @@ int mdimg_minmax_f32(const float* img, int n, int h, int w, const int32_t* sel, 
     return minmax_decode_run(mm, d, out_minmax, (cudaStream_t)stream);
 }
 
+int mdimg_mosaic_u8(const float* before, const float* after, uint8_t* out, int n, int h, int w,
+                    const int32_t* sel, int n_sel, int gap, int gap_level, void* ws, size_t ws_bytes,
+                    void* stream) {
+    if (bad_dims(n, h, w, sel, n_sel)) return MDIMG_ERR_INVALID;
+    Dims d = make_dims(n, h, w, sel, n_sel);
+    Arena a(ws, ws_bytes);
+    uint2* mm_b = a.take<uint2>(n);
+    uint2* mm_a = a.take<uint2>(n);
+    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "mosaic: workspace too small");
+    int rc = minmax_f32_run(before, d, mm_b, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = minmax_f32_run(after, d, mm_a, (cudaStream_t)stream);
+    if (rc) return rc;
+    return mosaic_u8_run(before, after, out, d, gap, gap_level, mm_b, mm_a, (cudaStream_t)stream);
+}
+
 int mdimg_normalize_u16(const uint16_t* in, float* out, int n, int h, int w, const int32_t* sel,
                         int n_sel, void* ws, size_t ws_bytes, void* stream) {
     if (bad_dims(n, h, w, sel, n_sel)) return MDIMG_ERR_INVALID;

@@ -31,6 +31,11 @@ int skip_flags_run(const Dims& d, const double* sigma, double thresh, int* skip,
 int blend_skip_run(const float* a, const float* b, float* out, const Dims& d, float c0, float c1,
                    const int* skip, int* skipped_out, cudaStream_t stream);
 int copy_run(const float* in, float* out, const Dims& d, cudaStream_t stream);
+// Before | after report mosaic in 8-bit gray (save_visuals, pipeline/dicom_io.py:99-126): each panel
+// autoscaled to its own min / max (mm_b, mm_a) and quantised like matplotlib's gray colormap.
+// out: device uint8 [n][h][2w + gap].
+int mosaic_u8_run(const float* before, const float* after, uint8_t* out, const Dims& d, int gap,
+                  int gap_level, const uint2* mm_b, const uint2* mm_a, cudaStream_t stream);
 
 // ---- unsharp.cu ----------------------------------------------------------------------------
 // weights: host array of radius+1 doubles (w[0] centre ... w[radius]); radius <= 12.

@@ -336,6 +336,50 @@ int clip01_run(const float* in, float* out, const Dims& d, cudaStream_t stream) 
     return check_launch("clip01");
 }
 
+namespace {
+// matplotlib's gray colormap on an autoscaled panel: Normalize in float32, 256 levels, the
+// level that lands on 256 (x == vmax) folded into 255; a flat panel maps to level 0.
+__device__ __forceinline__ uint8_t gray_level(float x, float vmin, float den) {
+    if (!(den > 0.0f)) return 0;
+    const float t = __fmul_rn(__fdiv_rn(__fsub_rn(x, vmin), den), 256.0f);
+    int l = (int)t;
+    l = l > 255 ? 255 : (l < 0 ? 0 : l);
+    return (uint8_t)l;
+}
+
+__global__ void __launch_bounds__(NT)
+k_mosaic_u8(const float* __restrict__ before, const float* __restrict__ after, uint8_t* __restrict__ out,
+            Dims d, int gap, int gap_level, const uint2* __restrict__ mm_b, const uint2* __restrict__ mm_a) {
+    const int s = slice_of(d.sel, blockIdx.y);
+    const float bmin = key2f(mm_b[s].x), bmax = key2f(mm_b[s].y);
+    const float amin = key2f(mm_a[s].x), amax = key2f(mm_a[s].y);
+    const float bden = (float)((double)bmax - (double)bmin), aden = (float)((double)amax - (double)amin);
+    const int ow = 2 * d.w + gap;
+    const long long total = (long long)d.h * ow;
+    const float* pb = before + (size_t)s * d.h * d.w;
+    const float* pa = after + (size_t)s * d.h * d.w;
+    uint8_t* o = out + (size_t)s * total;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+        const int y = (int)(i / ow), x = (int)(i - (long long)y * ow);
+        uint8_t v;
+        if (x < d.w) v = gray_level(pb[(size_t)y * d.w + x], bmin, bden);
+        else if (x < d.w + gap) v = (uint8_t)gap_level;
+        else v = gray_level(pa[(size_t)y * d.w + x - d.w - gap], amin, aden);
+        o[i] = v;
+    }
+}
+}  // namespace
+
+int mosaic_u8_run(const float* before, const float* after, uint8_t* out, const Dims& d, int gap,
+                  int gap_level, const uint2* mm_b, const uint2* mm_a, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    if (gap < 0 || gap > 1024) return set_error(MDIMG_ERR_INVALID, "mosaic: gap %d outside [0, 1024]", gap);
+    const long long total = (long long)d.h * (2LL * d.w + gap);
+    MDIMG_LAUNCH k_mosaic_u8<<<dim3(blocks_for(total, 8), d.n_sel), NT, 0, stream>>>(before, after, out, d, gap,
+                                                                               gap_level & 255, mm_b, mm_a);
+    return check_launch("mosaic");
+}
+
 int copy_run(const float* in, float* out, const Dims& d, cudaStream_t stream) {
     if (d.n_sel == 0) return MDIMG_OK;
     CopyF f;

@@ -1,13 +1,35 @@
 """``normalize_image`` — drop-in for ``pipeline/dicom_io.py:84-91`` (the windowing/normalisation
-step that produces the hot path's input).  File I/O, plotting and report text stay in the
-reference."""
+step that produces the hot path's input) — and ``save_visuals`` (``dicom_io.py:99-126``) as a GPU
+mosaic + PNG.  DICOM file parsing and report text stay in the reference."""
 
 from __future__ import annotations
+
+import os
+from typing import Dict
 
 import numpy as np
 import torch
 
+from .. import png
 from ..stack import get_ops
+
+
+def save_visuals(original: np.ndarray, enhanced: np.ndarray, out_dir: str, base_name: str) -> Dict[str, str]:
+    """Side-by-side before/after PNG, same signature and return value as the reference
+    (``{"before_after": path}``, file ``<base_name>_before_after.png``).  The reference renders a
+    matplotlib figure (titles, resampling to a 1500x750 canvas); this writes the two panels at native
+    resolution with matplotlib's gray colormap quantisation (each panel autoscaled to its own
+    min / max, 256 levels), computed on the GPU."""
+    a = np.ascontiguousarray(original, dtype=np.float32)
+    b = np.ascontiguousarray(enhanced, dtype=np.float32)
+    if a.ndim != 2 or a.shape != b.shape:
+        raise ValueError("save_visuals expects two 2-D images of the same shape")
+    ops = get_ops()
+    mosaic = ops.mosaic(torch.from_numpy(a[None]).to(ops.device), torch.from_numpy(b[None]).to(ops.device))
+    os.makedirs(out_dir, exist_ok=True)
+    figure_path = os.path.join(out_dir, f"{base_name}_before_after.png")
+    png.write_gray8(figure_path, mosaic[0].cpu().numpy())
+    return {"before_after": figure_path}
 
 
 def normalize_image(image: np.ndarray) -> np.ndarray:

@@ -160,6 +160,17 @@ class StackOps:
                    1 if monochrome1 else 0, 1 if raw.dtype == torch.int16 else 0, ws, wsb, self._stream())
         return out
 
+    def mosaic(self, before: torch.Tensor, after: torch.Tensor, gap: int = 8, gap_level: int = 255) -> torch.Tensor:
+        """[N, H, 2W + gap] uint8 before | after panels (matplotlib gray quantisation, per-panel autoscale)."""
+        n, h, w = self._img(before).shape
+        if tuple(self._img(after).shape) != (n, h, w):
+            raise ValueError("before / after stacks must have the same shape")
+        out = torch.empty((n, h, 2 * w + gap), dtype=torch.uint8, device=self.device)
+        ws, wsb = self._workspace(2 * (n * 8 + 256))
+        self._call(self.lib.mdimg_mosaic_u8, self._ptr(before), self._ptr(after), self._ptr(out), n, h, w,
+                   C.c_void_p(0), 0, int(gap), int(gap_level), ws, wsb, self._stream())
+        return out
+
     def minmax(self, img: torch.Tensor, sel=None) -> torch.Tensor:
         n, h, w = self._img(img).shape
         out = torch.zeros((n, 2), dtype=torch.float32, device=self.device)

@@ -338,3 +338,46 @@ def test_degenerate_inputs_metrics_and_validation(api, name):
             assert got[k] == pytest.approx(v, rel=2e-5, abs=2e-5, nan_ok=True), (name, k)
         else:
             assert got[k] == pytest.approx(v, rel=1e-5, abs=1e-9, nan_ok=True), (name, k)
+
+
+# ---- save_visuals (pipeline/dicom_io.py:99-126) as a GPU mosaic + PNG ---------------------------------
+def _gray_levels(x: np.ndarray) -> np.ndarray:
+    """matplotlib: Normalize() autoscaled to the panel (float32), gray colormap with N = 256."""
+    vmin, vmax = float(x.min()), float(x.max())
+    if vmax == vmin:
+        return np.zeros(x.shape, np.uint8)
+    t = (x - np.float32(vmin)) / np.float32(vmax - vmin)
+    xa = t * np.float32(256)
+    xa[xa == 256] = 255
+    return np.clip(xa.astype(int), 0, 255).astype(np.uint8)
+
+
+def test_save_visuals_writes_the_before_after_png(api, tmp_path, synthetic_image_noisy):
+    from PIL import Image
+    before = synthetic_image_noisy
+    after, _ = api.enhancement.apply_enhancements(before, ["noise", "low_contrast"])
+    out = api.dicom_io.save_visuals(before, after, str(tmp_path / "viz"), "case7")
+    assert list(out) == ["before_after"] and out["before_after"].endswith("case7_before_after.png")
+    img = np.array(Image.open(out["before_after"]))
+    h, w = before.shape
+    assert img.shape == (h, 2 * w + 8) and img.dtype == np.uint8
+    np.testing.assert_array_equal(img[:, :w], _gray_levels(before))
+    np.testing.assert_array_equal(img[:, w + 8:], _gray_levels(after))
+    assert (img[:, w:w + 8] == 255).all()
+
+
+def test_stack_visuals_one_launch_many_pngs(ops, synth, tmp_path):
+    import torch
+    from PIL import Image
+
+    from mdimg_b200.batch import save_stack_visuals
+    x = np.stack([omet.normalize_image(synth.ct_slice(1000 + z, z / 4, size=96)) for z in range(4)])
+    x[3] = 0.25                                                     # flat panel -> level 0
+    y = np.clip(x ** np.float32(0.8), 0, 1).astype(np.float32)
+    paths = save_stack_visuals(torch.from_numpy(x).to(ops.device), torch.from_numpy(y).to(ops.device),
+                               str(tmp_path), "vol", workers=2, gap=4)
+    assert len(paths) == 4
+    for z, p in enumerate(paths):
+        img = np.array(Image.open(p))
+        np.testing.assert_array_equal(img[:, :96], _gray_levels(x[z]))
+        np.testing.assert_array_equal(img[:, 100:], _gray_levels(y[z]))

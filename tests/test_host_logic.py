@@ -157,3 +157,19 @@ def test_gather_rows_gloo_world2(n_total):
         want = np.arange(n_total, dtype=np.float64)[:, None] * np.ones((1, 5))
         want[b0:] += 0.1
         np.testing.assert_allclose(out, want)
+
+
+def test_png_writer_roundtrips_through_pil():
+    """The report mosaics are written with a 30-line PNG encoder (zlib); PIL must read them back."""
+    import io
+
+    from PIL import Image
+
+    from mdimg_b200 import png
+    rng = np.random.default_rng(3)
+    for shape in [(1, 1), (37, 53), (64, 136)]:
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        got = np.array(Image.open(io.BytesIO(png.encode_gray8(a))))
+        assert got.dtype == np.uint8 and np.array_equal(got, a)
+    with pytest.raises(ValueError):
+        png.encode_gray8(np.zeros((4, 4), np.float32))

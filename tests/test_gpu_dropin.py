@@ -381,3 +381,37 @@ def test_stack_visuals_one_launch_many_pngs(ops, synth, tmp_path):
         img = np.array(Image.open(p))
         np.testing.assert_array_equal(img[:, :96], _gray_levels(x[z]))
         np.testing.assert_array_equal(img[:, 100:], _gray_levels(y[z]))
+
+
+def test_concurrent_callers_get_the_serial_results(api, synth):
+    """The reference's Flask backend runs pipelines on concurrent daemon threads
+    (backend/pipeline_runner.py:46-51): per-thread workspaces and streams keep callers independent."""
+    import threading
+    ims = [synth.fixture_noisy(), synth.fixture_low_contrast(), synth.fixture_clean(),
+           omet.normalize_image(synth.ct_slice(1000, 0.3, size=96))]
+    plan = synth.plan_full()
+
+    def work(im):
+        enh, labels = api.enhancement.apply_enhancements_from_params(im, plan)
+        return enh, labels, api.metrics.compute_metrics(enh), api.metrics.compute_validation(im, enh)["ssim"]
+
+    serial = [work(im) for im in ims]
+    results = [None] * len(ims)
+    errors = []
+
+    def runner(k):
+        try:
+            for _ in range(3):
+                results[k] = work(ims[k])
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=runner, args=(k,)) for k in range(len(ims))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (e0, l0, m0, s0), (e1, l1, m1, s1) in zip(serial, results):
+        np.testing.assert_array_equal(e0, e1)
+        assert l0 == l1 and m0 == m1 and s0 == s1

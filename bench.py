@@ -136,6 +136,12 @@ def run_reference(args) -> None:
 # GPU arm
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region.
+
+    NVML is read in-process (nvidia_ml_py) from a thread every 50 ms: two cheap driver calls per
+    sample.  A polling `nvidia-smi -lms` child was measurably intrusive here -- its start-up and its
+    multi-field queries stalled the second timed step by 10-100 ms -- and remains only the fallback."""
+
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -143,48 +149,106 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (monotonic time, sm_mhz, max_mhz, set of reason names)
+        self.thread = None
+        self._stop = threading.Event()
+        self.source = None
+
+    # ---- NVML in-process ----
+    def _nvml_loop(self, nv, handle):
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            mx = None
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM))
+                bits = int(get_reasons(handle))
+                self.lines.append((time.monotonic(), sm, mx, {n for b, n in names.items() if bits & b}))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.05)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            pass
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                ["nvidia-smi", f"--id={self._physical_index()}", f"--query-gpu={self.QUERY}",
                  "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except Exception:  # noqa: BLE001
+                pass
+        return self.index
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+    def wait_ready(self, timeout: float = 5.0) -> None:
+        """Block until the first sample has arrived (the sampler's start-up is over)."""
+        t_end = time.monotonic() + timeout
+        while self.thread is not None and not self.lines and time.monotonic() < t_end:
+            time.sleep(0.02)
+
+    def _pump(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.strip().split(",")]
             if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                sm, mx = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+            reasons = {n for n, v in zip(names, parts[5:9]) if v.lower().startswith("active")}
+            self.lines.append((time.monotonic(), sm, mx, reasons))
+
+    def stop(self, t0: float = float("-inf"), t1: float = float("inf")):
+        """Summary of the samples taken inside [t0, t1] (monotonic clock) -- the timed region."""
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        inside = [ln for ln in self.lines if t0 <= ln[0] <= t1]
+        if not inside:                      # region shorter than the sampling period: nearest samples
+            inside = self.lines[-2:]
+        sm = [ln[1] for ln in inside]
+        mx = [ln[2] for ln in inside if ln[2] is not None]
+        reasons = set()
+        for ln in inside:
+            reasons |= ln[3]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def measured_hbm_gbs():
@@ -249,20 +313,27 @@ def run_gpu(args) -> None:
         return res
 
     per_step = []
+    region = [0.0, 0.0]          # monotonic clock around the last timed region
 
     def timed(fn, steps, warmup):
+        last = None
         for _ in range(warmup):
-            fn()
+            # keep the previous result alive while the next step runs, exactly as the timed loop does:
+            # the caching allocator then reaches its steady state (two live result stacks) during
+            # warm-up instead of cudaMalloc-ing a second 1 GiB block inside the second timed step
+            last = fn()
         barrier()
         l0 = ops.lib.mdimg_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        region[0] = time.monotonic()
         e0.record()
         for i in range(steps):
             last = fn()
             marks[i].record()
         e1.record()
         barrier()
+        region[1] = time.monotonic()
         ms = e0.elapsed_time(e1)
         prev = e0
         per_step.clear()
@@ -277,9 +348,10 @@ def run_gpu(args) -> None:
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
     ms_total, launches, last = timed(step_resident, args.steps, args.warmup)
     steps_ms = list(per_step)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(region[0], region[1]) if rank == 0 else None
     ms_e2e, _, _ = timed(step_e2e, max(1, min(args.steps, 2)), 1)
     e2e_steps = max(1, min(args.steps, 2))
 

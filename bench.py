@@ -303,10 +303,11 @@ def run_gpu(args) -> None:
     # several chunks per stack so copies overlap compute; the first copy-in and the last copy-out
     # cannot overlap anything, so the chunks of the end-to-end path are smaller than the resident ones
     e2e_chunk = args.e2e_chunk or max(1, min(chunk, n // 8))
+    e2e_schedule = [int(v) for v in args.e2e_schedule.split(",")] if args.e2e_schedule else None
 
     def step_e2e():
         out, res = process_stack_host(stack, plan, chunk=e2e_chunk, ops=ops, pinned_in=pinned_in,
-                                      pinned_out=pinned_out, workers=args.workers)
+                                      pinned_out=pinned_out, workers=args.workers, schedule=e2e_schedule)
         if world > 1:
             rows = torch.from_numpy(res.packed).to(device)
             dist.all_gather_into_tensor(gathered, rows)
@@ -438,7 +439,8 @@ def main() -> None:
     ap.add_argument("--slices", type=int, default=1024, help="slices per GPU")
     ap.add_argument("--chunk", type=int, default=0, help="slices per chunk (0 = auto)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="slices per chunk of the end-to-end leg (0 = auto)")
-    ap.add_argument("--workers", type=int, default=2, help="host threads / CUDA streams driving chunks")
+    ap.add_argument("--e2e-schedule", default="", help="comma-separated chunk sizes of the end-to-end leg")
+    ap.add_argument("--workers", type=int, default=4, help="host threads / CUDA streams driving chunks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

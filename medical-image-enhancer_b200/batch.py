@@ -176,7 +176,7 @@ def _worker_streams(device: torch.device, count: int):
 def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
                        out_host: Optional[np.ndarray] = None, ops: Optional[StackOps] = None,
                        pinned_in: Optional[torch.Tensor] = None, pinned_out: Optional[torch.Tensor] = None,
-                       workers: int = 2):
+                       workers: int = 2, schedule: Optional[List[int]] = None):
     """End-to-end form with HOST buffers: per chunk, host->device copy of the raw slices, the whole
     pipeline on the GPU, device->host copy of the enhanced slices and of the result rows.
     `workers` host threads each drive every workers-th chunk with their own compute / copy-in /
@@ -184,6 +184,9 @@ def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
     trips inside a chunk (TV live-slice polls, safeguard decisions) never leave the GPU idle.
 
     raw_host: [N, H, W] uint16 or float32 numpy array (ideally backed by pinned memory).
+    schedule: optional list of chunk sizes (slices) in processing order, e.g. small first / last
+    chunks -- the first copy-in and the last copy-out cannot overlap any compute -- around large
+    ones; it is repeated / truncated to cover the stack.
     Returns (enhanced float32 host array, StackResult without device pixels)."""
     ops = ops or get_ops()
     n, h, w = raw_host.shape
@@ -198,7 +201,14 @@ def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
     else:
         out_t = torch.from_numpy(out_host)
     packed_host = torch.empty((n, PACK_COLS), dtype=torch.float64, pin_memory=True)
-    spans = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
+    if schedule:
+        spans, a, k = [], 0, 0
+        while a < n:
+            b = min(n, a + max(1, int(schedule[k % len(schedule)])))
+            spans.append((a, b))
+            a, k = b, k + 1
+    else:
+        spans = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
     workers = max(1, min(workers, len(spans)))
     labels: List[Optional[List[List[str]]]] = [None] * len(spans)
     caller = torch.cuda.current_stream(dev)

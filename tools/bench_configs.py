@@ -44,6 +44,40 @@ def main():
     ops = get_ops()
     out = {"hbm_peak_gbs": PEAK}
 
+    # ---- C1: one 512x512 slice through the drop-in functions (host numpy in / out), latency ----
+    import time
+
+    from mdimg_b200.pipeline import dicom_io as gio
+    from mdimg_b200.pipeline import enhancement as genh
+    from mdimg_b200.pipeline import metrics as gmet
+    raw1 = synth.ct_slice(1000, 0.0)
+    planf = synth.plan_full()
+
+    def c1_chain():
+        x = gio.normalize_image(raw1)
+        m = gmet.compute_metrics(x)
+        issues = gmet.detect_issues(m)
+        enh, labels = genh.apply_enhancements(x, issues)
+        val = gmet.compute_validation(x, enh)
+        return gmet.compute_objective_score(val)
+
+    def wall(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    x1 = gio.normalize_image(raw1)
+    out["C1"] = {
+        "deterministic_chain_ms": wall(c1_chain),          # normalize -> metrics -> issues -> enhance -> validate -> score
+        "compute_metrics_ms": wall(lambda: gmet.compute_metrics(x1)),
+        "apply_enhancements_from_params_P_full_ms": wall(lambda: genh.apply_enhancements_from_params(x1, planf)),
+        "compute_validation_ms": wall(lambda: gmet.compute_validation(x1, x1)),
+        "note": "wall-clock per call on one 512x512 slice, numpy in / numpy out (H2D + kernels + D2H)"}
+
     # ---- C3 ----
     base = [synth.radiograph(2000 + i) for i in range(min(n3, 8))]
     raw = np.stack([base[i % len(base)] for i in range(n3)])

@@ -415,7 +415,7 @@ def run_gpu(args) -> None:
                 "note": f"per loop body: 20 B/px (x 4 + p 8 read, p 8 written) x {chunk} slices x 512x512; one "
                         f"k_tvp launch runs two bodies and keeps the intermediate p in registers, so its "
                         f"DRAM traffic is about half the algorithmic figure (achieved can exceed the HBM peak); "
-                        f"measured limiter: FP32 pipe + issue, DRAM at 53 %; timed as (41 - 1 bodies) / 40 with "
+                        f"measured limiter: FP32 pipe + issue, DRAM at 55 %; timed as (41 - 1 bodies) / 40 with "
                         f"CUDA events; mean TV iterations/slice in the workload = {float(tv_iters.mean()):.1f}"}
         if not args.no_cpu:
             cores = len(os.sched_getaffinity(0))

@@ -121,3 +121,19 @@ def test_idempotence_and_fixed_points(ops, ct_stack):
     z = torch.empty_like(x)
     it = ops.tv_chambolle(x, z, 1e-6)
     assert float((z - x).abs().max()) < 1e-4 and int(it.max()) <= 200
+
+
+@pytest.mark.parametrize("shape,cap", [((3000, 3000), 5), ((1000, 1502), 8), ((513, 770), 11)])
+def test_tv_packed_kernels_at_radiograph_sizes(ops, synth, shape, cap):
+    """Strip grids far from the 512x512 case (row strips that do not divide the height, 50 column
+    strips, an odd height): the field after `cap` bodies equals the oracle's bit for bit."""
+    from oracle import restoration as ores
+    h, w = shape
+    base = omet.normalize_image(synth.radiograph(2000, 3000))
+    im = np.ascontiguousarray(base[:h, :w])
+    x = torch.from_numpy(im[None]).to(ops.device)
+    out = torch.empty_like(x)
+    iters = int(ops.tv_chambolle(x, out, 0.1, eps=0.0, max_iter=cap)[0].item())
+    ref, ref_iters = ores.denoise_tv_chambolle(im, 0.1, eps=0.0, max_num_iter=cap, return_iters=True)
+    assert iters == ref_iters == cap
+    np.testing.assert_array_equal(out[0].cpu().numpy(), ref)

@@ -283,7 +283,8 @@ def run_gpu(args) -> None:
     import torch.distributed as dist
 
     from mdimg_b200 import synth
-    from mdimg_b200.batch import PACK_COLS, default_chunk, process_stack, process_stack_host
+    from mdimg_b200.batch import (PACK_COLS, default_chunk, process_stack, process_stack_host,
+                                  tapered_schedule)
     from mdimg_b200.stack import get_ops
 
     rank = int(os.environ.get("RANK", "0"))
@@ -320,7 +321,12 @@ def run_gpu(args) -> None:
     # several chunks per stack so copies overlap compute; the first copy-in and the last copy-out
     # cannot overlap anything, so the chunks of the end-to-end path are smaller than the resident ones
     e2e_chunk = args.e2e_chunk or max(1, min(chunk, n // 8))
-    e2e_schedule = [int(v) for v in args.e2e_schedule.split(",")] if args.e2e_schedule else None
+    if args.e2e_schedule:
+        e2e_schedule = [int(v) for v in args.e2e_schedule.split(",")]
+    elif args.e2e_chunk:
+        e2e_schedule = None
+    else:
+        e2e_schedule = tapered_schedule(n, args.workers)
 
     def step_e2e():
         out, res = process_stack_host(stack, plan, chunk=e2e_chunk, ops=ops, pinned_in=pinned_in,
@@ -370,8 +376,8 @@ def run_gpu(args) -> None:
     ms_total, launches, last = timed(step_resident, args.steps, args.warmup)
     steps_ms = list(per_step)
     clocks = sampler.stop(region[0], region[1]) if rank == 0 else None
-    ms_e2e, _, _ = timed(step_e2e, max(1, min(args.steps, 2)), 1)
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, args.steps)
+    ms_e2e, _, _ = timed(step_e2e, e2e_steps, max(1, min(args.warmup, 2)))
 
     px_per_step = float(n) * H * W * world
     value = px_per_step * args.steps / (ms_total / 1e3) / 1e6
@@ -438,7 +444,8 @@ def run_gpu(args) -> None:
             "e2e": {"value": e2e_value, "unit": "Mpx/s",
                     "h2d_bytes_per_step": int(n * H * W * 2),
                     "d2h_bytes_per_step": int(n * H * W * 4 + n * PACK_COLS * 8),
-                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "chunk_slices": e2e_chunk},
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                    "chunk_slices": e2e_schedule if e2e_schedule else e2e_chunk},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu_base,

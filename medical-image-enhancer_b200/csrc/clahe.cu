@@ -292,16 +292,17 @@ k_clahe_final(Dims d, const int* __restrict__ status, const uint16_t* __restrict
         for (long long i = tid; i < n8; i += nthr) {
             const uint4 q = v8[i];
             float4 a, b;
-            a.x = __ldg(L + (q.x & 0xffffu)); a.y = __ldg(L + (q.x >> 16));
-            a.z = __ldg(L + (q.y & 0xffffu)); a.w = __ldg(L + (q.y >> 16));
-            b.x = __ldg(L + (q.z & 0xffffu)); b.y = __ldg(L + (q.z >> 16));
-            b.z = __ldg(L + (q.w & 0xffffu)); b.w = __ldg(L + (q.w >> 16));
+            // levels are <= 16383 by construction; the clamp only keeps a corrupted level in the table
+            a.x = __ldg(L + min(q.x & 0xffffu, NLEVELS - 1u)); a.y = __ldg(L + min(q.x >> 16, NLEVELS - 1u));
+            a.z = __ldg(L + min(q.y & 0xffffu, NLEVELS - 1u)); a.w = __ldg(L + min(q.y >> 16, NLEVELS - 1u));
+            b.x = __ldg(L + min(q.z & 0xffffu, NLEVELS - 1u)); b.y = __ldg(L + min(q.z >> 16, NLEVELS - 1u));
+            b.z = __ldg(L + min(q.w & 0xffffu, NLEVELS - 1u)); b.w = __ldg(L + min(q.w >> 16, NLEVELS - 1u));
             o4[2 * i] = a;
             o4[2 * i + 1] = b;
         }
-        for (long long i = (n8 << 3) + tid; i < len; i += nthr) o[i] = __ldg(L + v[i]);
+        for (long long i = (n8 << 3) + tid; i < len; i += nthr) o[i] = __ldg(L + min((unsigned)v[i], NLEVELS - 1u));
     } else {
-        for (long long i = tid; i < len; i += nthr) o[i] = __ldg(L + v[i]);
+        for (long long i = tid; i < len; i += nthr) o[i] = __ldg(L + min((unsigned)v[i], NLEVELS - 1u));
     }
 }
 

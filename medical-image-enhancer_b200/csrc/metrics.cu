@@ -86,6 +86,31 @@ __device__ __forceinline__ void hist_add(unsigned* h, int bin, bool valid, int l
     }
 }
 
+// Three histograms of the same pixel with ONE uniformity vote: in flat regions (every valid lane in
+// the same three bins) a warp issues three atomics in total; otherwise each lane adds its own.
+// v0 / v1 / v2: per-histogram validity (v1 and v2 are the pixel's validity, v0 adds the range test).
+__device__ __forceinline__ void hist_add3(unsigned* h0, int b0, bool v0, unsigned* h1, int b1, unsigned* h2, int b2,
+                                          bool valid, int lane) {
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+    if (mask == 0) return;
+    const int leader = __ffs(mask) - 1;
+    // pack (b0 | invalid flag, b1, b2) so that one shuffle broadcasts the leader's bins
+    const unsigned packed = ((v0 ? (unsigned)b0 : 0x3ffu) << 20) | ((unsigned)b1 << 10) | (unsigned)b2;
+    const unsigned lead = __shfl_sync(0xffffffffu, packed, leader);
+    if (__all_sync(0xffffffffu, !valid || packed == lead)) {
+        if (lane == leader) {
+            const unsigned n = (unsigned)__popc(mask);
+            if ((lead >> 20) != 0x3ffu) atomicAdd(&h0[lead >> 20], n);
+            atomicAdd(&h1[(lead >> 10) & 0x3ffu], n);
+            atomicAdd(&h2[lead & 0x3ffu], n);
+        }
+    } else if (valid) {
+        if (v0) atomicAdd(&h0[b0], 1u);
+        atomicAdd(&h1[b1], 1u);
+        atomicAdd(&h2[b2], 1u);
+    }
+}
+
 __global__ void __launch_bounds__(NT, 4)
 k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
                 float* __restrict__ gout, unsigned* __restrict__ l1x, unsigned* __restrict__ l1g) {
@@ -177,9 +202,9 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
                 c_gt1 += (xc > 1.0f);
             }
             // np.histogram(bins=256, range=(0,1)): exact power-of-two edges, out-of-range dropped
-            hist_add(sm.h256, b256, valid && xc >= 0.0f && xc <= 1.0f, lane);
-            hist_add(sm.hx, sel_bin1(xc), valid, lane);
-            hist_add(sm.hg, sel_bin1(g), valid, lane);
+            static_assert(SEL_L1_BINS <= 1024, "bins are packed into 10-bit fields");
+            hist_add3(sm.h256, b256, valid && xc >= 0.0f && xc <= 1.0f, sm.hx, sel_bin1(xc), sm.hg, sel_bin1(g),
+                      valid, lane);
             u0 = m0; u1 = m1; u2 = m2;
             m0 = n0; m1 = n1; m2 = n2;
             xc = xn;

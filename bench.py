@@ -423,7 +423,7 @@ def run_gpu(args) -> None:
                         f"DRAM traffic is about half the algorithmic figure (achieved can exceed the HBM peak); "
                         f"measured limiter: FP32 pipe + issue, DRAM at 55 %; timed as (41 - 1 bodies) / 40 with "
                         f"CUDA events; mean TV iterations/slice in the workload = {float(tv_iters.mean()):.1f}"}
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:     # the CPU leg is an N=1 measurement (rank 0 would share the host with 7 busy ranks)
             cores = len(os.sched_getaffinity(0))
             sample = max(4 * cores, 32)
             cpu_throughput(stack, cores, cores)          # warm the pool (not timed)

@@ -23,7 +23,7 @@ struct MetAcc {               // per slice, zero-initialised
     double sum_x, sum_x2, sum_lap, sum_lap2, sum_abslap, sum_g, sum_g2, sum_ls, sum_ls2;
     double sum_strong;
     double box16[2];          // sum lv, sum lv^2 (NIQE)
-    unsigned long long cnt_low, cnt_high, cnt_lt0, cnt_gt1, cnt_edge, cnt_strong;
+    unsigned long long cnt_low, cnt_high, cnt_edge, cnt_strong;
     unsigned gmax_key;
     unsigned dd_zero;         // number of exactly-zero 'dd' coefficients
     unsigned hist256[256];
@@ -156,7 +156,7 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
     }
 
     // ---- D: 3x3 stencils ----
-    unsigned c_low = 0, c_high = 0, c_lt0 = 0, c_gt1 = 0;
+    unsigned c_low = 0, c_high = 0;
     float gmax = 0.0f;
     float f_lap = 0.0f, f_lap2 = 0.0f, f_abs = 0.0f, f_g = 0.0f, f_g2 = 0.0f;
     double d_x = 0.0, d_x2 = 0.0;
@@ -198,8 +198,6 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
                 f_g2 = fmaf(g, g, f_g2);
                 c_low += (xc <= 0.01f);
                 c_high += (xc >= 0.99f);
-                c_lt0 += (xc < 0.0f);
-                c_gt1 += (xc > 1.0f);
             }
             // np.histogram(bins=256, range=(0,1)): exact power-of-two edges, out-of-range dropped
             static_assert(SEL_L1_BINS <= 1024, "bins are packed into 10-bit fields");
@@ -217,13 +215,11 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
 
     block_sum<9>(acc_v, sm.red);
     MetAcc* A = acc + si;
-    unsigned cl = warp_sum_u(c_low), ch = warp_sum_u(c_high), c0 = warp_sum_u(c_lt0), c1 = warp_sum_u(c_gt1);
+    unsigned cl = warp_sum_u(c_low), ch = warp_sum_u(c_high);
     float gm = warp_max(gmax);
     if (lane == 0) {
         if (cl) atomicAdd(&A->cnt_low, (unsigned long long)cl);
         if (ch) atomicAdd(&A->cnt_high, (unsigned long long)ch);
-        if (c0) atomicAdd(&A->cnt_lt0, (unsigned long long)c0);
-        if (c1) atomicAdd(&A->cnt_gt1, (unsigned long long)c1);
         atomicMax(&A->gmax_key, f2key(gm));
     }
     if (tid == 0) {

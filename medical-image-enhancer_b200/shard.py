@@ -43,3 +43,14 @@ def gather_rows(rows: torch.Tensor, n_total: int, group: Optional[dist.ProcessGr
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def gather_labels(labels, group: Optional[dist.ProcessGroup] = None):
+    """Applied-operation label lists of every rank, concatenated in slice_range order (python
+    objects over the process group's object channel; a few bytes per slice, needed only where the
+    gathered rows are persisted or reported, pipeline/storage.py)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return list(labels)
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, list(labels), group=group)
+    return [l for part in parts for l in part]

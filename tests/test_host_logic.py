@@ -13,7 +13,7 @@ import torch
 from scipy import ndimage as ndi
 
 from mdimg_b200 import engine
-from mdimg_b200.shard import gather_rows, slice_range
+from mdimg_b200.shard import gather_labels, gather_rows, slice_range
 from mdimg_b200.stack import bilateral_spatial, gaussian_taps, percentile_plan
 from oracle import ref_enhancement as oenh
 from oracle import ref_metrics as omet
@@ -132,7 +132,8 @@ def _gloo_worker(rank, world, n_total, port, q):
     a, b = slice_range(n_total, rank, world)
     rows = torch.arange(a, b, dtype=torch.float64)[:, None] * torch.ones((1, 5), dtype=torch.float64) + rank / 10
     out = gather_rows(rows, n_total)
-    q.put((rank, out.numpy()))
+    labels = gather_labels([[f"slice{i}", f"rank{rank}"] for i in range(a, b)])
+    q.put((rank, (out.numpy(), labels)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -152,7 +153,8 @@ def test_gather_rows_gloo_world2(n_total):
         assert p.exitcode == 0
     a0, b0 = slice_range(n_total, 0, 2)
     for r in range(2):
-        out = results[r]
+        out, labels = results[r]
+        assert labels == [[f"slice{i}", f"rank{0 if i < b0 else 1}"] for i in range(n_total)]
         assert out.shape == (n_total, 5)
         want = np.arange(n_total, dtype=np.float64)[:, None] * np.ones((1, 5))
         want[b0:] += 0.1

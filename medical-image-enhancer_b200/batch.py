@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import threading
 from dataclasses import dataclass
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -194,82 +194,94 @@ def _worker_streams(device: torch.device, count: int):
     return _stream_cache[key]
 
 
-def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
-                       out_host: Optional[np.ndarray] = None, ops: Optional[StackOps] = None,
-                       pinned_in: Optional[torch.Tensor] = None, pinned_out: Optional[torch.Tensor] = None,
-                       workers: int = 2, schedule: Optional[List[int]] = None):
-    """End-to-end form with HOST buffers: per chunk, host->device copy of the raw slices, the whole
-    pipeline on the GPU, device->host copy of the enhanced slices and of the result rows.
-    `workers` host threads each drive every workers-th chunk with their own compute / copy-in /
-    copy-out streams: copies of one chunk overlap the compute of the others, and the host round
-    trips inside a chunk (TV live-slice polls, safeguard decisions) never leave the GPU idle.
-
-    raw_host: [N, H, W] uint16 or float32 numpy array (ideally backed by pinned memory).
-    schedule: optional list of chunk sizes (slices) in processing order, e.g. small first / last
-    chunks -- the first copy-in and the last copy-out cannot overlap any compute -- around large
-    ones; it is repeated / truncated to cover the stack.
-    Returns (enhanced float32 host array, StackResult without device pixels)."""
-    ops = ops or get_ops()
-    n, h, w = raw_host.shape
-    chunk = chunk or default_chunk(h, w)
-    dev = ops.device
-    if raw_host.dtype == np.uint16:
-        src_t = pinned_in if pinned_in is not None else torch.from_numpy(raw_host.view(np.int16))
-    else:
-        src_t = pinned_in if pinned_in is not None else torch.from_numpy(np.ascontiguousarray(raw_host, np.float32))
-    if out_host is None:
-        out_t = pinned_out if pinned_out is not None else torch.empty((n, h, w), dtype=torch.float32, pin_memory=True)
-    else:
-        out_t = torch.from_numpy(out_host)
-    packed_host = torch.empty((n, PACK_COLS), dtype=torch.float64, pin_memory=True)
+def _spans_of(n: int, chunk: int, schedule: Optional[List[int]]):
     if schedule:
         spans, a, k = [], 0, 0
         while a < n:
             b = min(n, a + max(1, int(schedule[k % len(schedule)])))
             spans.append((a, b))
             a, k = b, k + 1
-    else:
-        spans = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
-    workers = max(1, min(workers, len(spans)))
-    labels: List[Optional[List[List[str]]]] = [None] * len(spans)
+        return spans
+    return [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
+
+
+def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[int] = None,
+                        out_hosts: Optional[Sequence[Optional[np.ndarray]]] = None, ops: Optional[StackOps] = None,
+                        pinned_ins: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                        pinned_outs: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                        workers: int = 2, schedule: Optional[List[int]] = None):
+    """End-to-end form with HOST buffers for a SEQUENCE of stacks (a cohort of volumes): per chunk,
+    host->device copy of the raw slices, the whole pipeline on the GPU, device->host copy of the
+    enhanced slices and of the result rows.  `workers` host threads claim chunks dynamically, each
+    with its own compute / copy-in / copy-out streams: copies of one chunk overlap the compute of
+    the others, and the host round trips inside a chunk (TV live-slice polls, safeguard decisions)
+    never leave the GPU idle.  The chunks of all stacks form ONE queue: a worker that finishes the
+    last chunk of stack k goes straight on to stack k+1, so the copy-out of a stack's last chunks --
+    which nothing inside that stack can overlap -- runs under the next stack's compute; only the
+    final stack's tail is exposed.
+
+    raw_hosts[k]: [N, H, W] uint16 or float32 numpy array (ideally backed by pinned memory;
+    `pinned_ins[k]` is the same data as a pinned int16 / float32 tensor).  Output buffers may be
+    shared between stacks that are at least two apart (double buffering).
+    schedule: optional list of chunk sizes (slices) in processing order, applied per stack.
+    Returns a list of (enhanced float32 host array, StackResult without device pixels)."""
+    ops = ops or get_ops()
+    dev = ops.device
+    nstk = len(raw_hosts)
+    srcs, outs, packs, jobs, labels = [], [], [], [], []
+    for k, raw_host in enumerate(raw_hosts):
+        n, h, w = raw_host.shape
+        pin = pinned_ins[k] if pinned_ins is not None else None
+        if pin is not None:
+            src_t = pin
+        elif raw_host.dtype == np.uint16:
+            src_t = torch.from_numpy(raw_host.view(np.int16))
+        else:
+            src_t = torch.from_numpy(np.ascontiguousarray(raw_host, np.float32))
+        out_np = out_hosts[k] if out_hosts is not None else None
+        pout = pinned_outs[k] if pinned_outs is not None else None
+        if out_np is not None:
+            out_t = torch.from_numpy(out_np)
+        else:
+            out_t = pout if pout is not None else torch.empty((n, h, w), dtype=torch.float32, pin_memory=True)
+        srcs.append(src_t)
+        outs.append(out_t)
+        packs.append(torch.empty((n, PACK_COLS), dtype=torch.float64, pin_memory=True))
+        spans = _spans_of(n, chunk or default_chunk(h, w), schedule)
+        labels.append([None] * len(spans))
+        jobs.extend((k, j, a, b) for j, (a, b) in enumerate(spans))
+    workers = max(1, min(workers, len(jobs)))
     caller = torch.cuda.current_stream(dev)
     ready = torch.cuda.Event()
     ready.record(caller)
     errors: List[BaseException] = []
-    next_chunk = [0]
+    next_job = [0]
     queue_lock = threading.Lock()
 
-    def worker(k: int) -> None:
+    def worker(wk: int) -> None:
         try:
             with torch.cuda.device(dev):
-                main, copy_in, copy_out = _host_streams(dev, k)
-                staged = {}
-
-                def stage(i):
-                    a, b = spans[i]
-                    with torch.cuda.stream(copy_in):
-                        t = src_t[a:b].to(dev, non_blocking=True)
-                        ev = torch.cuda.Event()
-                        ev.record(copy_in)
-                    staged[i] = (t, ev)
+                main, copy_in, copy_out = _host_streams(dev, wk)
 
                 def take():                       # chunks are handed out dynamically, in order
                     with queue_lock:
-                        i = next_chunk[0]
-                        next_chunk[0] += 1
-                    return i if i < len(spans) else None
+                        i = next_job[0]
+                        next_job[0] += 1
+                    return jobs[i] if i < len(jobs) else None
 
                 copy_in.wait_event(ready)
                 main.wait_event(ready)
-                cur_i = take()
+                job = take()
                 with torch.cuda.stream(main):
-                    while cur_i is not None:
+                    while job is not None:
                         # a worker claims its next chunk only when it is done with the current one
                         # (the safeguard read-backs pace the host thread with the GPU), so chunks
                         # are balanced dynamically; its copy-in overlaps the other workers' compute
-                        stage(cur_i)
-                        a, b = spans[cur_i]
-                        raw_d, ev = staged.pop(cur_i)
+                        k, j, a, b = job
+                        with torch.cuda.stream(copy_in):
+                            raw_d = srcs[k][a:b].to(dev, non_blocking=True)
+                            ev = torch.cuda.Event()
+                            ev.record(copy_in)
                         main.wait_event(ev)
                         raw_d.record_stream(main)
                         enh, packed, lab = process_chunk(ops, raw_d, plan, True)
@@ -277,12 +289,12 @@ def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
                         done.record(main)
                         with torch.cuda.stream(copy_out):
                             copy_out.wait_event(done)
-                            out_t[a:b].copy_(enh, non_blocking=True)
-                            packed_host[a:b].copy_(packed, non_blocking=True)
+                            outs[k][a:b].copy_(enh, non_blocking=True)
+                            packs[k][a:b].copy_(packed, non_blocking=True)
                             enh.record_stream(copy_out)
                             packed.record_stream(copy_out)
-                        labels[cur_i] = lab
-                        cur_i = take()
+                        labels[k][j] = lab
+                        job = take()
                 copy_out.synchronize()
                 main.synchronize()
         except BaseException as exc:  # noqa: BLE001 - re-raised on the caller's thread
@@ -291,16 +303,28 @@ def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
     if workers == 1:
         worker(0)
     else:
-        threads = [threading.Thread(target=worker, args=(k,), daemon=True) for k in range(workers)]
+        threads = [threading.Thread(target=worker, args=(wk,), daemon=True) for wk in range(workers)]
         for t in threads:
             t.start()
         for t in threads:
             t.join()
     if errors:
         raise errors[0]
-    flat = [lab for part in labels for lab in (part or [])]
-    res = StackResult(enhanced=None, packed=packed_host.numpy().copy(), labels=flat)
-    return out_t.numpy(), res
+    results = []
+    for k in range(nstk):
+        flat = [lab for part in labels[k] for lab in (part or [])]
+        results.append((outs[k].numpy(), StackResult(enhanced=None, packed=packs[k].numpy().copy(), labels=flat)))
+    return results
+
+
+def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
+                       out_host: Optional[np.ndarray] = None, ops: Optional[StackOps] = None,
+                       pinned_in: Optional[torch.Tensor] = None, pinned_out: Optional[torch.Tensor] = None,
+                       workers: int = 2, schedule: Optional[List[int]] = None):
+    """One stack through `process_stacks_host`.  Returns (enhanced float32 host array, StackResult)."""
+    return process_stacks_host([raw_host], plan, chunk=chunk, out_hosts=[out_host], ops=ops,
+                               pinned_ins=[pinned_in], pinned_outs=[pinned_out], workers=workers,
+                               schedule=schedule)[0]
 
 
 _host_stream_cache: dict = {}

@@ -231,6 +231,29 @@ def test_stack_pipeline_matches_per_slice_calls(ops, synth):
         assert isinstance(res.score(z)[0], float)
 
 
+def test_cohort_pipeline_equals_stack_by_stack(ops, synth):
+    """A sequence of stacks through one chunk queue (process_stacks_host) gives each stack the result
+    of its own process_stack_host call; shared (double-buffered) outputs are honoured."""
+    from mdimg_b200.batch import process_stack_host, process_stacks_host
+    stacks = [np.stack([synth.ct_slice(3000 + 16 * v + z, z / 5, size=128) for z in range(5 + v)]) for v in range(3)]
+    plan = synth.plan_full()
+    single = [process_stack_host(s.copy(), plan, chunk=2, ops=ops, workers=2) for s in stacks]
+    single = [(o.copy(), r) for o, r in single]
+    cohort = process_stacks_host(stacks, plan, chunk=2, ops=ops, workers=3, schedule=[3, 2, 1])
+    assert len(cohort) == 3
+    for (o1, r1), (o2, r2), s in zip(single, cohort, stacks):
+        assert o2.shape == s.shape and o2.dtype == np.float32
+        np.testing.assert_array_equal(o1, o2)
+        np.testing.assert_allclose(r1.packed, r2.packed, rtol=1e-9, atol=1e-12)
+        assert r1.labels == r2.labels and len(r2.labels) == s.shape[0]
+    # caller-provided output arrays
+    outs = [np.empty(s.shape, np.float32) for s in stacks]
+    again = process_stacks_host(stacks, plan, chunk=4, ops=ops, out_hosts=outs, workers=2)
+    for (o1, _), o3, (o4, _) in zip(single, outs, again):
+        np.testing.assert_array_equal(o1, o3)
+        assert o4 is o3 or np.shares_memory(o4, o3)
+
+
 def test_score_plans_matches_the_tool_loop(ops, images, synth):
     """K candidate plans x N images (pipeline/tools.py:95-183 semantics) vs the oracle run one by one."""
     import torch

@@ -161,10 +161,18 @@ k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* _
             int step = under / n_excess;
             if (step < 1) step = 1;
             int cnt = 0;
+            if (step == 1) {                   // warp-uniform; the usual case under heavy clipping: no modulo
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int j = lane + 32 * m;
-                if (j >= index && ((j - index) % step) == 0 && hv[m] < clim) { hv[m] += 1; cnt += 1; }
+                for (int m = 0; m < 8; ++m) {
+                    const int j = lane + 32 * m;
+                    if (j >= index && hv[m] < clim) { hv[m] += 1; cnt += 1; }
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const int j = lane + 32 * m;
+                    if (j >= index && ((j - index) % step) == 0 && hv[m] < clim) { hv[m] += 1; cnt += 1; }
+                }
             }
             n_excess -= __reduce_add_sync(0xffffffffu, cnt);
             if (n_excess <= 0) break;
@@ -191,7 +199,18 @@ k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* _
     }
 }
 
-constexpr int BW = 64, BH = 4;   // blend tile: 256 threads, one pixel each, rows of 64
+// Blend tile: 128 columns x 32 rows per block of 256 threads.  A thread owns four adjacent columns
+// and walks four rows (warp w: rows w, w + 8, ...): everything that depends on the column only --
+// block index, position inside the block, the two interpolation weights, the offsets of the two
+// neighbouring regions' LUTs -- is computed once per thread, what depends on the row only once per
+// warp and row, and the per-block setup (k float64 divisions for np.arange(k) / k) is shared by
+// 4096 pixels.  Per pixel remain the four LUT gathers and the float64 products in skimage's order.
+constexpr int BPX = 4, BW = 32 * BPX, BROWS = 4, BH = WARPS * BROWS;
+
+// uint16 LUT entry -> float64 without an integer conversion: (2^52 + m) - 2^52, exact for m < 2^32
+__device__ __forceinline__ double u2d(unsigned m) {
+    return __dsub_rn(__hiloint2double(0x43300000, (int)m), 4503599627370496.0);
+}
 
 __global__ void __launch_bounds__(NT)
 k_clahe_blend(Dims d, ClaheGeom g, SliceRange* __restrict__ rng, const int* __restrict__ status,
@@ -209,43 +228,76 @@ k_clahe_blend(Dims d, ClaheGeom g, SliceRange* __restrict__ rng, const int* __re
         icoef[threadIdx.x] = __dsub_rn(1.0, c);
     }
     __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int tiles_x = (d.w + BW - 1) / BW;
     const int bx = blockIdx.x % tiles_x, by = blockIdx.x / tiles_x;
-    const int x = bx * BW + (threadIdx.x & (BW - 1));
-    const int y = by * BH + (threadIdx.x / BW);
+    const int x0 = bx * BW + lane * BPX;
+    // ---- per column: map_array is the LUT grid edge-padded by one: entry j -> region clamp(j - 1) ----
+    double wx0[BPX], wx1[BPX];
+    int o0[BPX], o1[BPX];
+#pragma unroll
+    for (int c = 0; c < BPX; ++c) {
+        const int px = x0 + c + k / 2;
+        const int bxk = px / k, ix = px - bxk * k;
+        o0[c] = min(max(bxk - 1, 0), g.ntx - 1) * NBINS;
+        o1[c] = min(bxk, g.ntx - 1) * NBINS;
+        wx0[c] = icoef[ix];
+        wx1[c] = coef[ix];
+    }
+    const size_t img = (size_t)si * d.h * d.w;
+    const uint16_t* mbase = maps + (size_t)si * g.nty * g.ntx * NBINS;
+    const bool vec = (d.w % BPX) == 0 && x0 + BPX <= d.w;       // 4 bins in one 32-bit load, 4 levels in one 64-bit store
     unsigned vmin = 0xFFFFFFFFu, vmax = 0u;
-    if (x < d.w && y < d.h) {
-        const size_t o = (size_t)y * d.w + x;
-        const int b = bins[(size_t)si * d.h * d.w + o];
-        const int py = y + k / 2, px = x + k / 2;
-        // floor(p / k) for k <= 48, p < 2^20: the fractional part of p / k is a multiple of 1 / k,
-        // far from the float32 rounding error of (p + 0.5) * (1 / k)
-        const float rk = __frcp_rn((float)k);
-        const int byk = (int)(((float)py + 0.5f) * rk), iy = py - byk * k;
-        const int bxk = (int)(((float)px + 0.5f) * rk), ix = px - bxk * k;
-        // map_array is the LUT grid edge-padded by one: entry j -> region clamp(j - 1)
-        const int t0y = min(max(byk - 1, 0), g.nty - 1), t1y = min(byk, g.nty - 1);
-        const int t0x = min(max(bxk - 1, 0), g.ntx - 1), t1x = min(bxk, g.ntx - 1);
-        const uint16_t* mbase = maps + (size_t)si * g.nty * g.ntx * NBINS;
-        const double wy0 = icoef[iy], wy1 = coef[iy], wx0 = icoef[ix], wx1 = coef[ix];
-        float acc = 0.0f;
-        acc = __fadd_rn(acc, (float)__dmul_rn((double)mbase[((size_t)t0y * g.ntx + t0x) * NBINS + b], __dmul_rn(wx0, wy0)));
-        acc = __fadd_rn(acc, (float)__dmul_rn((double)mbase[((size_t)t0y * g.ntx + t1x) * NBINS + b], __dmul_rn(wx1, wy0)));
-        acc = __fadd_rn(acc, (float)__dmul_rn((double)mbase[((size_t)t1y * g.ntx + t0x) * NBINS + b], __dmul_rn(wx0, wy1)));
-        acc = __fadd_rn(acc, (float)__dmul_rn((double)mbase[((size_t)t1y * g.ntx + t1x) * NBINS + b], __dmul_rn(wx1, wy1)));
-        const unsigned v = (unsigned)acc;      // astype(uint16): truncation
-        vout[(size_t)si * d.h * d.w + o] = (uint16_t)v;
-        vmin = v; vmax = v;
+#pragma unroll
+    for (int j = 0; j < BROWS; ++j) {
+        const int y = by * BH + wid + WARPS * j;
+        if (y >= d.h || x0 >= d.w) continue;
+        // ---- per row (warp-uniform) ----
+        const int py = y + k / 2;
+        const int byk = py / k, iy = py - byk * k;
+        const uint16_t* m0 = mbase + (size_t)min(max(byk - 1, 0), g.nty - 1) * g.ntx * NBINS;
+        const uint16_t* m1 = mbase + (size_t)min(byk, g.nty - 1) * g.ntx * NBINS;
+        const double wy0 = icoef[iy], wy1 = coef[iy];
+        const size_t o = img + (size_t)y * d.w + x0;
+        unsigned b4;
+        if (vec) {
+            b4 = *reinterpret_cast<const unsigned*>(bins + o);
+        } else {
+            b4 = 0;
+#pragma unroll
+            for (int c = 0; c < BPX; ++c)
+                if (x0 + c < d.w) b4 |= (unsigned)bins[o + c] << (8 * c);
+        }
+        unsigned v4[BPX];
+#pragma unroll
+        for (int c = 0; c < BPX; ++c) {
+            const unsigned b = (b4 >> (8 * c)) & 0xffu;
+            float acc = 0.0f;
+            acc = __fadd_rn(acc, (float)__dmul_rn(u2d(m0[o0[c] + b]), __dmul_rn(wx0[c], wy0)));
+            acc = __fadd_rn(acc, (float)__dmul_rn(u2d(m0[o1[c] + b]), __dmul_rn(wx1[c], wy0)));
+            acc = __fadd_rn(acc, (float)__dmul_rn(u2d(m1[o0[c] + b]), __dmul_rn(wx0[c], wy1)));
+            acc = __fadd_rn(acc, (float)__dmul_rn(u2d(m1[o1[c] + b]), __dmul_rn(wx1[c], wy1)));
+            v4[c] = (unsigned)acc;             // astype(uint16): truncation
+            if (x0 + c < d.w) { vmin = min(vmin, v4[c]); vmax = max(vmax, v4[c]); }
+        }
+        if (vec) {
+            *reinterpret_cast<uint2*>(vout + o) = make_uint2(v4[0] | (v4[1] << 16), v4[2] | (v4[3] << 16));
+        } else {
+#pragma unroll
+            for (int c = 0; c < BPX; ++c)
+                if (x0 + c < d.w) vout[o + c] = (uint16_t)v4[c];
+        }
     }
     vmin = __reduce_min_sync(0xffffffffu, vmin);
     vmax = __reduce_max_sync(0xffffffffu, vmax);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) { smin[wid] = vmin; smax[wid] = vmax; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < WARPS; ++w) { vmin = min(vmin, smin[w]); vmax = max(vmax, smax[w]); }
-        atomicMin(&rng[si].vmin, vmin);
-        atomicMax(&rng[si].vmax, vmax);
+        if (vmin <= vmax) {
+            atomicMin(&rng[si].vmin, vmin);
+            atomicMax(&rng[si].vmax, vmax);
+        }
     }
 }
 

@@ -61,7 +61,8 @@ enum mdimg_op {
     MDIMG_OP_LIGHT_DENOISE = 10,
     MDIMG_OP_BILATERAL = 11,
     MDIMG_OP_TV = 12,        /* param = max_iter */
-    MDIMG_OP_MINMAX = 13
+    MDIMG_OP_MINMAX = 13,
+    MDIMG_OP_VALIDATION = 14
 };
 
 const char* mdimg_last_error(void);
@@ -125,6 +126,17 @@ int mdimg_quality(const float* img, int n, int h, int w, const int32_t* sel, int
 int mdimg_fullref(const float* original, const float* enhanced, int n, int h, int w,
                   const int32_t* sel, int n_sel, double* out, void* ws, size_t ws_bytes,
                   void* stream);
+
+/* The image-sized work of compute_validation (pipeline/metrics.py:225-259) in one call:
+ * compute_metrics + NIQE approximation + edge ratio of both images, SSIM and PSNR.  out: device
+ * double[n][MDIMG_VALIDATION_COLS] = metrics row of the original [MDIMG_METRIC_COLS] | of the
+ * enhanced image [MDIMG_METRIC_COLS] | ssim | psnr; the scalar gains and pass logic
+ * (metrics.py:261-329) are host arithmetic on that row.  Percentile plan as for mdimg_metrics.
+ * Workspace: MDIMG_OP_VALIDATION. */
+#define MDIMG_VALIDATION_COLS (2 * MDIMG_METRIC_COLS + 2)
+int mdimg_validation(const float* original, const float* enhanced, int n, int h, int w,
+                     const int32_t* sel, int n_sel, const int32_t* pct_lo, const int32_t* pct_hi,
+                     const float* pct_gamma, double* out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- enhancement steps ------------------------------------------------------------------ */
 /* denoise_wavelet(image, channel_axis=None, rescale_sigma=True, mode=...[, sigma=...])

@@ -17,9 +17,10 @@ LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
 MDIMG_OK = 0
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE = 1, 2, 3, 4
 METRIC_COLS = 24
+VALIDATION_COLS = 2 * METRIC_COLS + 2
 
 OP_NORMALIZE, OP_METRICS, OP_SIGMA, OP_QUALITY, OP_FULLREF, OP_WAVELET, OP_CLAHE, OP_GAMMA, \
-    OP_UNSHARP, OP_LIGHT_DENOISE, OP_BILATERAL, OP_TV, OP_MINMAX = range(1, 14)
+    OP_UNSHARP, OP_LIGHT_DENOISE, OP_BILATERAL, OP_TV, OP_MINMAX, OP_VALIDATION = range(1, 15)
 
 _p = C.c_void_p
 _i = C.c_int
@@ -47,6 +48,8 @@ PROTOTYPES = {
     "mdimg_estimate_sigma": (_i, [_p, *_IMG, _p, *_WS]),
     "mdimg_quality": (_i, [_p, *_IMG, _i, _p, *_WS]),
     "mdimg_fullref": (_i, [_p, _p, *_IMG, _p, *_WS]),
+    "mdimg_validation": (_i, [_p, _p, *_IMG, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                              _p, *_WS]),
     "mdimg_wavelet_denoise": (_i, [_p, _p, *_IMG, _i, _p, _d, _p, *_WS]),
     "mdimg_clahe": (_i, [_p, _p, *_IMG, _d, _i, _p, *_WS]),
     "mdimg_clahe_gamma": (_i, [_p, _p, *_IMG, _d, _i, _d, _p, *_WS]),

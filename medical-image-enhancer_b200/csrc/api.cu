@@ -48,6 +48,16 @@ bool bad_dims(int n, int h, int w, const int32_t* sel, int n_sel) {
 
 size_t mm_bytes(int n) { Arena a(nullptr, 0); a.take<uint2>(n); return a.off; }
 
+struct ValidationBufs { double* rows_a; double* rows_b; double* fr; void* sub; size_t sub_bytes; };
+void carve_validation(Arena& a, int n, int h, int w, ValidationBufs& b) {
+    b.rows_a = a.take<double>((size_t)n * MC_COLS);
+    b.rows_b = a.take<double>((size_t)n * MC_COLS);
+    b.fr = a.take<double>((size_t)n * 2);
+    const size_t m = metrics_workspace_bytes(n, h, w), f = fullref_workspace_bytes(n, h, w);
+    b.sub_bytes = m > f ? m : f;                  // the three calls run one after another on the stream
+    b.sub = a.take<char>(b.sub_bytes);
+}
+
 struct LightBufs { double* sigma; int* skip; float* tmp; void* sws; size_t sws_bytes; void* wws; size_t wws_bytes; };
 void carve_light(Arena& a, int n, int n_sel, int h, int w, LightBufs& b) {
     b.sigma = a.take<double>(n);
@@ -114,6 +124,12 @@ size_t mdimg_workspace_bytes(int op, int n, int h, int w, int param) {
         case MDIMG_OP_SIGMA: return sigma_workspace_bytes(n, h, w);
         case MDIMG_OP_QUALITY: return quality_workspace_bytes(n, h, w);
         case MDIMG_OP_FULLREF: return fullref_workspace_bytes(n, h, w);
+        case MDIMG_OP_VALIDATION: {
+            Arena a(nullptr, 0);
+            ValidationBufs b;
+            carve_validation(a, n, h, w, b);
+            return a.off;
+        }
         case MDIMG_OP_WAVELET: return wavelet_workspace_bytes(n, n, h, w);
         case MDIMG_OP_CLAHE: return mm_bytes(n) + clahe_workspace_bytes(n, n, h, w, param);
         case MDIMG_OP_GAMMA:
@@ -231,6 +247,24 @@ int mdimg_fullref(const float* original, const float* enhanced, int n, int h, in
     if (bad_dims(n, h, w, sel, n_sel)) return MDIMG_ERR_INVALID;
     Dims d = make_dims(n, h, w, sel, n_sel);
     return fullref_run(original, enhanced, d, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int mdimg_validation(const float* original, const float* enhanced, int n, int h, int w,
+                     const int32_t* sel, int n_sel, const int32_t* pct_lo, const int32_t* pct_hi,
+                     const float* pct_gamma, double* out, void* ws, size_t ws_bytes, void* stream) {
+    if (bad_dims(n, h, w, sel, n_sel)) return MDIMG_ERR_INVALID;
+    Arena a(ws, ws_bytes);
+    ValidationBufs b;
+    carve_validation(a, n, h, w, b);
+    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "validation: workspace too small (%zu > %zu)", a.off, ws_bytes);
+    int rc = mdimg_metrics(original, n, h, w, sel, n_sel, 1, pct_lo, pct_hi, pct_gamma, b.rows_a, b.sub, b.sub_bytes, stream);
+    if (rc) return rc;
+    rc = mdimg_metrics(enhanced, n, h, w, sel, n_sel, 1, pct_lo, pct_hi, pct_gamma, b.rows_b, b.sub, b.sub_bytes, stream);
+    if (rc) return rc;
+    rc = mdimg_fullref(original, enhanced, n, h, w, sel, n_sel, b.fr, b.sub, b.sub_bytes, stream);
+    if (rc) return rc;
+    Dims d = make_dims(n, h, w, sel, n_sel);
+    return validation_pack_run(d, b.rows_a, b.rows_b, b.fr, out, (cudaStream_t)stream);
 }
 
 int mdimg_wavelet_denoise(const float* in, float* out, int n, int h, int w, const int32_t* sel,

@@ -156,7 +156,29 @@ __global__ void k_fullref_out(Dims d, const double* __restrict__ acc2, double* _
     out[s * 2 + 1] = 10.0 * log10(1.0 / mse);   // +inf when the images are identical
 }
 
+__global__ void k_validation_pack(Dims d, const double* __restrict__ ra, const double* __restrict__ rb,
+                                  const double* __restrict__ fr, double* __restrict__ out) {
+    constexpr int W = 2 * MC_COLS + 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_sel * W) return;
+    const int si = i / W, c = i - si * W;
+    const int s = slice_of(d.sel, si);
+    double v;
+    if (c < MC_COLS) v = ra[(size_t)s * MC_COLS + c];
+    else if (c < 2 * MC_COLS) v = rb[(size_t)s * MC_COLS + c - MC_COLS];
+    else v = fr[(size_t)s * 2 + c - 2 * MC_COLS];
+    out[(size_t)s * W + c] = v;
+}
+
 }  // namespace
+
+int validation_pack_run(const Dims& d, const double* rows_a, const double* rows_b, const double* fr,
+                        double* out, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    const int total = d.n_sel * (2 * MC_COLS + 2);
+    MDIMG_LAUNCH k_validation_pack<<<(total + 255) / 256, 256, 0, stream>>>(d, rows_a, rows_b, fr, out);
+    return check_launch("validation");
+}
 
 void launch_box16_stats(const float* img, const Dims& d, double* acc2, cudaStream_t stream) {
     static bool attr_set = false;

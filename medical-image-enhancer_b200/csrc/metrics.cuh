@@ -44,6 +44,10 @@ size_t fullref_workspace_bytes(int n_sel, int h, int w);
 int fullref_run(const float* a, const float* b, const Dims& d, double* out, void* ws,
                 size_t ws_bytes, cudaStream_t stream);
 
+// out[s] = rows_a[s] (MC_COLS) | rows_b[s] (MC_COLS) | fr[s] (2) for the selected slices.
+int validation_pack_run(const Dims& d, const double* rows_a, const double* rows_b, const double* fr,
+                        double* out, cudaStream_t stream);
+
 // Shared by metrics.cu / fullref.cu: box-16 local-variance statistics (NIQE, metrics.py:195-200).
 // acc2: device [n_sel][2] doubles (sum lv, sum lv^2), must be zeroed by the caller.
 void launch_box16_stats(const float* img, const Dims& d, double* acc2, cudaStream_t stream);

@@ -428,6 +428,10 @@ class Engine:
         """Device rows needed by compute_validation: metrics (with NIQE / edge ratio) of both
         stacks and (ssim, psnr).  Metrics of the same stack are computed once (the reference
         recomputes identical values, pipeline/metrics.py:229-236,272)."""
+        if rows_before is None and rows_after is None:      # one library call (mdimg_validation)
+            v = self.ops.validation(original, enhanced)
+            k = v.shape[1] // 2 - 1
+            return v[:, :k], v[:, k:2 * k], v[:, 2 * k:]
         if rows_before is None:
             rows_before = self.ops.metrics(original, with_niqe=True)
         if rows_after is None:

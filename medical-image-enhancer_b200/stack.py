@@ -224,6 +224,21 @@ class StackOps:
                    self._ptr(out), ws, wsb, self._stream())
         return out
 
+    def validation(self, original: torch.Tensor, enhanced: torch.Tensor, sel=None) -> torch.Tensor:
+        """[N, 50] float64 in one library call: metrics row (with NIQE) of the original | of the
+        enhanced image | ssim | psnr -- the image-sized work of compute_validation."""
+        n, h, w = self._img(original).shape
+        if tuple(self._img(enhanced).shape) != (n, h, w):
+            raise ValueError("Input images must have the same dimensions.")
+        lo, hi, gamma = percentile_plan(h * w)
+        out = torch.full((n, _lib.VALIDATION_COLS), float("nan"), dtype=torch.float64, device=self.device)
+        ws, wsb = self._ws_for(_lib.OP_VALIDATION, n, h, w)
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_validation, self._ptr(original), self._ptr(enhanced), n, h, w, sp, ns,
+                   lo.ctypes.data_as(C.POINTER(C.c_int32)), hi.ctypes.data_as(C.POINTER(C.c_int32)),
+                   gamma.ctypes.data_as(C.POINTER(C.c_float)), self._ptr(out), ws, wsb, self._stream())
+        return out
+
     # ---- enhancement steps --------------------------------------------------------------------
     def wavelet_denoise(self, src, dst, mode: str = "soft", sigma: Optional[torch.Tensor] = None,
                         sigma_scale: float = 1.0, sel=None):

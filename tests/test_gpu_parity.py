@@ -118,6 +118,26 @@ def test_ssim_psnr(ops, dev, images, name):
     assert fr[1] == pytest.approx(float(peak_signal_noise_ratio(im, other, data_range=1.0)), rel=1e-9)
 
 
+def test_validation_call_equals_its_three_parts(ops, dev, images):
+    """mdimg_validation = mdimg_metrics (original) | mdimg_metrics (enhanced) | mdimg_fullref, also on a
+    subset of slices."""
+    import torch
+    names = [k for k in NAMES if images[k].shape == images["clean64"].shape]
+    a = torch.from_numpy(np.stack([images[k] for k in names])).to(ops.device)
+    b = (a * 0.9 + 0.05 * a.flip(0)).contiguous()
+    got = ops.validation(a, b).cpu().numpy()
+    want = np.concatenate([ops.metrics(a, with_niqe=True).cpu().numpy(), ops.metrics(b, with_niqe=True).cpu().numpy(),
+                           ops.fullref(a, b).cpu().numpy()], axis=1)
+    assert got.shape == (len(names), 50)
+    # float64 accumulators are combined with atomics: equal to rounding of the sums
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12, equal_nan=True)
+    if len(names) > 1:
+        sel = torch.tensor([len(names) - 1], dtype=torch.int32, device=ops.device)
+        part = ops.validation(a, b, sel=sel).cpu().numpy()
+        np.testing.assert_allclose(part[-1], want[-1], rtol=1e-9, atol=1e-12, equal_nan=True)
+        assert np.isnan(part[0]).all()
+
+
 def test_ssim_of_identical_images(ops, dev, images):
     fr = ops.fullref(dev(images["clean64"]), dev(images["clean64"]))[0].cpu().numpy()
     assert fr[0] == pytest.approx(1.0) and np.isinf(fr[1])

@@ -41,23 +41,42 @@ template <int XW, int XH, int HL, int REFLECT, typename Store>
 __device__ __forceinline__ void load_tile(const float* __restrict__ src, int h, int w, int x0, int y0,
                                           Store&& store) {
     static_assert(XW <= 96, "at most three columns per lane");
+    constexpr int NC = (XW + 31) / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    int gx[3];
+    int gx[NC];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int c = lane + 32 * k;
-        const int x = x0 + c - HL;
+    for (int k = 0; k < NC; ++k) {
+        const int x = x0 + lane + 32 * k - HL;
         gx[k] = REFLECT == 0 ? refl_sym_fast(x, w) : refl_mirror(x, w);
     }
-    for (int r = wid; r < XH; r += nw) {
+    auto row_of = [&](int r) {
         const int y = y0 + r - HL;
         const int gy = REFLECT == 0 ? refl_sym_fast(y, h) : refl_mirror(y, h);
-        const float* row = src + (size_t)gy * w;
+        return src + (size_t)gy * w;
+    };
+    // four rows per trip: their (up to 12) loads are issued before the first shared-memory store, so the
+    // tile load is not one dependent load -> store round trip per row
+    int r = wid;
+    for (; r + 3 * nw < XH; r += 4 * nw) {
+        float v[4][NC];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int c = lane + 32 * k;
-            if (c < XW) store(r, c, row[gx[k]]);
+        for (int u = 0; u < 4; ++u) {
+            const float* row = row_of(r + u * nw);
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (lane + 32 * k < XW) v[u][k] = row[gx[k]];
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (lane + 32 * k < XW) store(r + u * nw, lane + 32 * k, v[u][k]);
+    }
+    for (; r < XH; r += nw) {
+        const float* row = row_of(r);
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+            if (lane + 32 * k < XW) store(r, lane + 32 * k, row[gx[k]]);
     }
 }
 

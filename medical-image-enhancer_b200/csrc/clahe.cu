@@ -111,9 +111,38 @@ k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* _
     uint8_t* bdst = bins + (size_t)si * d.h * d.w;
     const uint8_t* lut = binlut + (size_t)si * NU16;
     const int kk = k * k;
-    // lane -> (row, column) inside the region, advanced by 32 elements per trip without divisions
     int ry = lane / k, rx = lane - ry * k;
     const int dry = 32 / k, drx = 32 - dry * k;
+    if (drx == 0 && kk >= 32) {
+        // k = 8, 16, 32: a trip covers whole rows, so a lane keeps its column (index, mirror, bounds
+        // test) for the whole region, and the trips are independent of each other: eight pixel loads,
+        // then eight table gathers are in flight at a time instead of one dependent load -> gather ->
+        // atomic chain per trip
+        const int ox = tx * k + rx, gx = mirror_fast(ox, d.w);
+        const bool in_w = ox < d.w;
+        const int trips = kk >> 5;
+        for (int t0 = 0; t0 < trips; t0 += 8) {
+            float v[8];
+            int b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u < trips) {
+                    const int gy = mirror_fast(ty * k + ry + (t0 + u) * dry, d.h);
+                    v[u] = src[(size_t)gy * d.w + gx];
+                }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u < trips) b[u] = lut[to_u16(v[u])];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u < trips) {
+                    const int oy = ty * k + ry + (t0 + u) * dry;
+                    atomicAdd(&h[b[u]], 1);
+                    if (oy < d.h && in_w) bdst[(size_t)oy * d.w + ox] = (uint8_t)b[u];
+                }
+        }
+    } else
+    // lane -> (row, column) inside the region, advanced by 32 elements per trip without divisions
     for (int i = lane; i < kk; i += 32) {
         const int oy = ty * k + ry, ox = tx * k + rx;        // padded index minus pad_start
         const int gy = mirror_fast(oy, d.h), gx = mirror_fast(ox, d.w);

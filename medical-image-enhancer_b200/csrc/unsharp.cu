@@ -19,11 +19,29 @@ constexpr int MAXR = 12;
 
 struct GaussW { double w[MAXR + 1]; };   // passed by value: re-entrant across streams
 
+// scipy's symmetric correlate1d on a window of 2R + 1 doubles (centre at win[R]).
+template <int R>
+__device__ __forceinline__ double gauss_window(const double (&win)[2 * R + 1], const GaussW& gw) {
+    double acc = __dmul_rn(win[R], gw.w[0]);
+#pragma unroll
+    for (int j = R; j >= 1; --j)
+        acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(win[R - j], win[R + j]), gw.w[j]));
+    return acc;
+}
+
+// Both passes slide a register window of 2R + 1 doubles along the filter axis, so every tile element
+// is converted float32 -> float64 once per pass instead of once per tap (the conversion pipe, not
+// the float64 pipe, was this kernel's limiter: 2 (2R + 1) + 2 conversions per pixel).
+//   axis 0: thread = (column, row segment), walks down its segment;
+//   axis 1: lane = row, warp = 8-column segment, walks right; the result is parked in the input
+//           tile (each thread overwrites only the pixel it alone reads) and written out coalesced.
 template <int R>
 __global__ void __launch_bounds__(NT)
 k_unsharp(const float* __restrict__ in, float* __restrict__ out, Dims d, float amount,
           const uint2* __restrict__ mm, const GaussW gw) {
-    constexpr int XW = TW + 2 * R, XH = TH + 2 * R, XP = XW + 1;
+    constexpr int XW = TW + 2 * R, XH = TH + 2 * R, XP = XW | 1, W = 2 * R + 1;
+    constexpr int NSEG = NT / XW, RS = (TH + NSEG - 1) / NSEG;
+    static_assert(NSEG >= 1 && TH == 32 && TW == 8 * (NT / 32), "pass layout");
     __shared__ float X[XH][XP];
     __shared__ float V[TH][XP];
     const int s = slice_of(d.sel, blockIdx.y);
@@ -37,13 +55,40 @@ k_unsharp(const float* __restrict__ in, float* __restrict__ out, Dims d, float a
 
     load_tile<XW, XH, R, 0>(src, d.h, d.w, x0, y0, [&](int r, int c, float v) { X[r][c] = v; });
     __syncthreads();
-    for (int i = tid; i < TH * XW; i += NT) {
-        int r = i / XW, c = i - r * XW;
-        double acc = __dmul_rn((double)X[r + R][c], gw.w[0]);
+    if (tid < XW * NSEG) {
+        const int sg = tid / XW, c = tid - sg * XW;
+        const int r0 = sg * RS;
+        double win[W];
 #pragma unroll
-        for (int j = R; j >= 1; --j)
-            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)X[r + R - j][c], (double)X[r + R + j][c]), gw.w[j]));
-        V[r][c] = (float)acc;
+        for (int k = 0; k < W - 1; ++k) win[k + 1] = (double)X[min(r0 + k, XH - 1)][c];
+#pragma unroll
+        for (int t = 0; t < RS; ++t) {
+            const int r = r0 + t;
+            if (r < TH) {
+#pragma unroll
+                for (int k = 0; k < W - 1; ++k) win[k] = win[k + 1];
+                win[W - 1] = (double)X[r + 2 * R][c];
+                V[r][c] = (float)gauss_window<R>(win, gw);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int r = lane, c0 = wid * 8;
+        double win[W];
+#pragma unroll
+        for (int k = 0; k < W - 1; ++k) win[k + 1] = (double)V[r][c0 + k];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int c = c0 + t;
+#pragma unroll
+            for (int k = 0; k < W - 1; ++k) win[k] = win[k + 1];
+            win[W - 1] = (double)V[r][c + 2 * R];
+            const float blurred = (float)gauss_window<R>(win, gw);
+            const float x = X[r + R][c + R];
+            float res = __fadd_rn(x, __fmul_rn(__fsub_rn(x, blurred), amount));
+            X[r + R][c + R] = fminf(fmaxf(res, lo), 1.0f);
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -52,17 +97,7 @@ k_unsharp(const float* __restrict__ in, float* __restrict__ out, Dims d, float a
         for (int i2 = 0; i2 < TW / 32; ++i2) {
             const int r = wid + 8 * j2, c = lane + 32 * i2;
             const int gy = y0 + r, gx = x0 + c;
-            if (gy < d.h && gx < d.w) {
-                double acc = __dmul_rn((double)V[r][c + R], gw.w[0]);
-#pragma unroll
-                for (int j = R; j >= 1; --j)
-                    acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)V[r][c + R - j], (double)V[r][c + R + j]), gw.w[j]));
-                const float blurred = (float)acc;
-                const float x = X[r + R][c + R];
-                float res = __fadd_rn(x, __fmul_rn(__fsub_rn(x, blurred), amount));
-                res = fminf(fmaxf(res, lo), 1.0f);
-                dst[(size_t)gy * d.w + gx] = res;
-            }
+            if (gy < d.h && gx < d.w) dst[(size_t)gy * d.w + gx] = X[r + R][c + R];
         }
 }
 

@@ -205,32 +205,35 @@ __device__ __forceinline__ void refine_visit(RefineCtx& c, float f, bool valid) 
 template <bool ABS>
 __device__ __forceinline__ void refine_stream(RefineCtx& c, const float* __restrict__ v, int len, int tid, int nthr) {
     const int lane = c.lane;
-    if ((((uintptr_t)v) & 15) == 0) {
-        const int n4 = len >> 2;
-        const float4* v4 = reinterpret_cast<const float4*>(v);
-        int i = tid;
-        // four independent 128-bit loads in flight while the whole warp is in range (warp-uniform test)
-        for (; i - lane + 31 + 3 * nthr < n4; i += 4 * nthr) {
-            const float4 a = v4[i], b = v4[i + nthr], d = v4[i + 2 * nthr], e = v4[i + 3 * nthr];
-            refine_visit<ABS>(c, a.x, true); refine_visit<ABS>(c, a.y, true); refine_visit<ABS>(c, a.z, true); refine_visit<ABS>(c, a.w, true);
-            refine_visit<ABS>(c, b.x, true); refine_visit<ABS>(c, b.y, true); refine_visit<ABS>(c, b.z, true); refine_visit<ABS>(c, b.w, true);
-            refine_visit<ABS>(c, d.x, true); refine_visit<ABS>(c, d.y, true); refine_visit<ABS>(c, d.z, true); refine_visit<ABS>(c, d.w, true);
-            refine_visit<ABS>(c, e.x, true); refine_visit<ABS>(c, e.y, true); refine_visit<ABS>(c, e.z, true); refine_visit<ABS>(c, e.w, true);
-        }
-        for (; i - lane < n4; i += nthr) {
-            const bool ok = i < n4;
-            const float4 q = ok ? v4[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            refine_visit<ABS>(c, q.x, ok); refine_visit<ABS>(c, q.y, ok); refine_visit<ABS>(c, q.z, ok); refine_visit<ABS>(c, q.w, ok);
-        }
-        for (int k = (n4 << 2) + tid; k - lane < len; k += nthr) {
-            const bool ok = k < len;
-            refine_visit<ABS>(c, ok ? v[k] : 0.0f, ok);
-        }
-    } else {
-        for (int i = tid; i - lane < len; i += nthr) {
-            const bool ok = i < len;
-            refine_visit<ABS>(c, ok ? v[i] : 0.0f, ok);
-        }
+    // head: the 0..3 elements in front of the first 16-byte boundary (slices of odd length -- the 257 x 257
+    // 'dd' band of a 512 x 512 image -- start at any 4-byte offset), then 128-bit loads, then the tail
+    int head = (int)(((16u - (unsigned)((uintptr_t)v & 15u)) & 15u) >> 2);
+    if (head > len) head = len;
+    if (tid - lane < head) {                       // first warp of the slice only (warp-uniform)
+        const bool ok = tid < head;
+        refine_visit<ABS>(c, ok ? v[tid] : 0.0f, ok);
+    }
+    const float* va = v + head;
+    const int rem = len - head;
+    const int n4 = rem >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(va);
+    int i = tid;
+    // four independent 128-bit loads in flight while the whole warp is in range (warp-uniform test)
+    for (; i - lane + 31 + 3 * nthr < n4; i += 4 * nthr) {
+        const float4 a = v4[i], b = v4[i + nthr], d = v4[i + 2 * nthr], e = v4[i + 3 * nthr];
+        refine_visit<ABS>(c, a.x, true); refine_visit<ABS>(c, a.y, true); refine_visit<ABS>(c, a.z, true); refine_visit<ABS>(c, a.w, true);
+        refine_visit<ABS>(c, b.x, true); refine_visit<ABS>(c, b.y, true); refine_visit<ABS>(c, b.z, true); refine_visit<ABS>(c, b.w, true);
+        refine_visit<ABS>(c, d.x, true); refine_visit<ABS>(c, d.y, true); refine_visit<ABS>(c, d.z, true); refine_visit<ABS>(c, d.w, true);
+        refine_visit<ABS>(c, e.x, true); refine_visit<ABS>(c, e.y, true); refine_visit<ABS>(c, e.z, true); refine_visit<ABS>(c, e.w, true);
+    }
+    for (; i - lane < n4; i += nthr) {
+        const bool ok = i < n4;
+        const float4 q = ok ? v4[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        refine_visit<ABS>(c, q.x, ok); refine_visit<ABS>(c, q.y, ok); refine_visit<ABS>(c, q.z, ok); refine_visit<ABS>(c, q.w, ok);
+    }
+    for (int k = (n4 << 2) + tid; k - lane < rem; k += nthr) {
+        const bool ok = k < rem;
+        refine_visit<ABS>(c, ok ? va[k] : 0.0f, ok);
     }
     __syncwarp();
     if (lane < c.qn) refine_account(c, c.q[lane], 0u);            // leftovers

@@ -254,6 +254,31 @@ def test_cohort_pipeline_equals_stack_by_stack(ops, synth):
         assert o4 is o3 or np.shares_memory(o4, o3)
 
 
+def test_empty_single_and_ragged_stacks(ops, synth):
+    """Zero slices, one slice, and a cohort whose stacks differ in slice count AND image size."""
+    import torch
+    from mdimg_b200.batch import PACK_COLS, process_stack, process_stack_host, process_stacks_host
+    plan = synth.plan_full()
+    empty = np.zeros((0, 64, 64), np.uint16)
+    res = process_stack(torch.from_numpy(empty.view(np.int16)).to(ops.device), plan)
+    assert res.packed.shape == (0, PACK_COLS) and res.labels == [] and tuple(res.enhanced.shape) == (0, 64, 64)
+    out, res_h = process_stack_host(empty, plan, ops=ops)
+    assert out.shape == (0, 64, 64) and res_h.packed.shape == (0, PACK_COLS) and res_h.labels == []
+    one = synth.ct_slice(4100, 0.3, size=96)[None]
+    small = np.stack([synth.ct_slice(4200 + z, z / 3, size=64) for z in range(3)])
+    wide = np.stack([synth.ct_slice(4300 + z, z / 2, size=128)[:94, :] for z in range(2)])     # 94 x 128
+    cohort = process_stacks_host([one, empty, small, wide], plan, chunk=2, ops=ops, workers=3)
+    assert [o.shape for o, _ in cohort] == [one.shape, empty.shape, small.shape, wide.shape]
+    for stack, (o, r) in zip([one, empty, small, wide], cohort):
+        assert len(r.labels) == stack.shape[0] and r.packed.shape == (stack.shape[0], PACK_COLS)
+        for z in range(stack.shape[0]):
+            x = omet.normalize_image(stack[z])
+            ref, ref_labels = oenh.apply_enhancements_from_params(x, plan)
+            assert r.labels[z] == ref_labels
+            assert float((np.abs(o[z].astype(np.float64) - ref) > LSB16).mean()) < 0.01
+            assert r.metrics_before(z)["entropy"] == pytest.approx(omet.compute_metrics(x)["entropy"], rel=1e-9)
+
+
 def test_score_plans_matches_the_tool_loop(ops, images, synth):
     """K candidate plans x N images (pipeline/tools.py:95-183 semantics) vs the oracle run one by one."""
     import torch

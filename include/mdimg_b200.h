@@ -189,6 +189,12 @@ int mdimg_axpby(const float* a, const float* b, float* out, int n, int h, int w,
 /* np.clip(x, 0, 1) (pipeline/enhancement.py:218,225,314,352,360,367). */
 int mdimg_clip01(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
                  void* stream);
+/* 16-bit export of an enhanced [0, 1] stack: uint16(clip(rint(float32(x) * 65535), 0, 65535)), i.e.
+ * skimage's img_as_uint (the conversion equalize_adapthist applies to its input,
+ * pipeline/enhancement.py:183).  The reference itself returns float32 (pipeline/enhancement.py:226,368);
+ * this halves the device-to-host bytes of a stack for callers that store 16-bit pixels. */
+int mdimg_export_u16(const float* in, uint16_t* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                     void* stream);
 int mdimg_copy(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
                void* stream);
 

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "mdimg_axpby": (_i, [_p, _p, _p, *_IMG, _d, _d, _i, _p]),
     "mdimg_clip01": (_i, [_p, _p, *_IMG, _p]),
     "mdimg_copy": (_i, [_p, _p, *_IMG, _p]),
+    "mdimg_export_u16": (_i, [_p, _p, *_IMG, _p]),
 }
 
 _lock = threading.Lock()

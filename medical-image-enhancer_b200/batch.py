@@ -209,7 +209,7 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
                         out_hosts: Optional[Sequence[Optional[np.ndarray]]] = None, ops: Optional[StackOps] = None,
                         pinned_ins: Optional[Sequence[Optional[torch.Tensor]]] = None,
                         pinned_outs: Optional[Sequence[Optional[torch.Tensor]]] = None,
-                        workers: int = 2, schedule: Optional[List[int]] = None):
+                        workers: int = 2, schedule: Optional[List[int]] = None, out_dtype=np.float32):
     """End-to-end form with HOST buffers for a SEQUENCE of stacks (a cohort of volumes): per chunk,
     host->device copy of the raw slices, the whole pipeline on the GPU, device->host copy of the
     enhanced slices and of the result rows.  `workers` host threads claim chunks dynamically, each
@@ -224,7 +224,15 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
     `pinned_ins[k]` is the same data as a pinned int16 / float32 tensor).  Output buffers may be
     shared between stacks that are at least two apart (double buffering).
     schedule: optional list of chunk sizes (slices) in processing order, applied per stack.
-    Returns a list of (enhanced float32 host array, StackResult without device pixels)."""
+    out_dtype: np.float32 (the reference's return type) or np.uint16 -- the 16-bit export
+    ``uint16(clip(rint(x * 65535), 0, 65535))`` formed on the device (`mdimg_export_u16`), which halves the
+    device-to-host bytes; metrics, validation rows and labels are those of the float32 image either way.
+    Returns a list of (enhanced host array, StackResult without device pixels)."""
+    out_dtype = np.dtype(out_dtype)
+    if out_dtype not in (np.dtype(np.float32), np.dtype(np.uint16)):
+        raise ValueError("out_dtype must be float32 or uint16")
+    as_u16 = out_dtype == np.dtype(np.uint16)
+    t_dtype = torch.int16 if as_u16 else torch.float32          # uint16 bit pattern in an int16 tensor
     ops = ops or get_ops()
     dev = ops.device
     nstk = len(raw_hosts)
@@ -241,9 +249,13 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
         out_np = out_hosts[k] if out_hosts is not None else None
         pout = pinned_outs[k] if pinned_outs is not None else None
         if out_np is not None:
-            out_t = torch.from_numpy(out_np)
+            if out_np.dtype != out_dtype or out_np.shape != (n, h, w):
+                raise ValueError(f"output array {k}: expected {out_dtype} {(n, h, w)}, got {out_np.dtype} {out_np.shape}")
+            out_t = torch.from_numpy(out_np.view(np.int16) if as_u16 else out_np)
         else:
-            out_t = pout if pout is not None else torch.empty((n, h, w), dtype=torch.float32, pin_memory=True)
+            out_t = pout if pout is not None else torch.empty((n, h, w), dtype=t_dtype, pin_memory=True)
+            if out_t.dtype != t_dtype:
+                raise ValueError(f"pinned output {k}: expected a {t_dtype} tensor")
         srcs.append(src_t)
         outs.append(out_t)
         packs.append(torch.empty((n, PACK_COLS), dtype=torch.float64, pin_memory=True))
@@ -285,6 +297,8 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
                         main.wait_event(ev)
                         raw_d.record_stream(main)
                         enh, packed, lab = process_chunk(ops, raw_d, plan, True)
+                        if as_u16:
+                            enh = ops.export_u16(enh)
                         done = torch.cuda.Event()
                         done.record(main)
                         with torch.cuda.stream(copy_out):
@@ -313,18 +327,20 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
     results = []
     for k in range(nstk):
         flat = [lab for part in labels[k] for lab in (part or [])]
-        results.append((outs[k].numpy(), StackResult(enhanced=None, packed=packs[k].numpy().copy(), labels=flat)))
+        out_np = outs[k].numpy()
+        results.append((out_np.view(np.uint16) if as_u16 else out_np,
+                        StackResult(enhanced=None, packed=packs[k].numpy().copy(), labels=flat)))
     return results
 
 
 def process_stack_host(raw_host: np.ndarray, plan, chunk: Optional[int] = None,
                        out_host: Optional[np.ndarray] = None, ops: Optional[StackOps] = None,
                        pinned_in: Optional[torch.Tensor] = None, pinned_out: Optional[torch.Tensor] = None,
-                       workers: int = 2, schedule: Optional[List[int]] = None):
-    """One stack through `process_stacks_host`.  Returns (enhanced float32 host array, StackResult)."""
+                       workers: int = 2, schedule: Optional[List[int]] = None, out_dtype=np.float32):
+    """One stack through `process_stacks_host`.  Returns (enhanced host array, StackResult)."""
     return process_stacks_host([raw_host], plan, chunk=chunk, out_hosts=[out_host], ops=ops,
                                pinned_ins=[pinned_in], pinned_outs=[pinned_out], workers=workers,
-                               schedule=schedule)[0]
+                               schedule=schedule, out_dtype=out_dtype)[0]
 
 
 _host_stream_cache: dict = {}

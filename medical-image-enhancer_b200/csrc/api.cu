@@ -380,6 +380,13 @@ int mdimg_clip01(const float* in, float* out, int n, int h, int w, const int32_t
     return clip01_run(in, out, d, (cudaStream_t)stream);
 }
 
+int mdimg_export_u16(const float* in, uint16_t* out, int n, int h, int w, const int32_t* sel, int n_sel,
+                     void* stream) {
+    if (bad_dims(n, h, w, sel, n_sel)) return MDIMG_ERR_INVALID;
+    Dims d = make_dims(n, h, w, sel, n_sel);
+    return export_u16_run(in, out, d, (cudaStream_t)stream);
+}
+
 int mdimg_copy(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
                void* stream) {
     if (bad_dims(n, h, w, sel, n_sel)) return MDIMG_ERR_INVALID;

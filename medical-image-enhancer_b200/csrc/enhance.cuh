@@ -26,6 +26,8 @@ int gamma_run(const float* in, float* out, const Dims& d, double gamma, const ui
 int axpby_run(const float* a, const float* b, float* out, const Dims& d, float c0, float c1,
               int clip01, cudaStream_t stream);
 int clip01_run(const float* in, float* out, const Dims& d, cudaStream_t stream);
+// uint16(clip(rint(x * 65535), 0, 65535)) of the selected slices (16-bit export of an enhanced stack).
+int export_u16_run(const float* in, uint16_t* out, const Dims& d, cudaStream_t stream);
 // skip[s] = sigma[s] < thresh (device int[n]);  blend: out = skip ? a : c0*a + c1*b
 int skip_flags_run(const Dims& d, const double* sigma, double thresh, int* skip, cudaStream_t stream);
 int blend_skip_run(const float* a, const float* b, float* out, const Dims& d, float c0, float c1,

@@ -329,6 +329,41 @@ int skip_flags_run(const Dims& d, const double* sigma, double thresh, int* skip,
     return check_launch("skip_flags");
 }
 
+namespace {
+// 16-bit export of a [0, 1] float32 stack: skimage's img_as_uint on float input,
+// uint16(clip(rint(float32(x) * 65535), 0, 65535)) -- round half to even, as numpy's rint.
+__device__ __forceinline__ unsigned export_level(float x) {
+    const float t = fminf(fmaxf(rintf(__fmul_rn(x, 65535.0f)), 0.0f), 65535.0f);
+    return (unsigned)t;
+}
+
+__global__ void __launch_bounds__(NT)
+k_export_u16(const float* __restrict__ in, uint16_t* __restrict__ out, Dims d) {
+    const int s = slice_of(d.sel, blockIdx.y);
+    const long long len = d.px();
+    const float* p = in + (size_t)s * len;
+    uint16_t* o = out + (size_t)s * len;
+    const long long tid = (long long)blockIdx.x * NT + threadIdx.x, nthr = (long long)gridDim.x * NT;
+    if ((len & 3) == 0 && (((uintptr_t)p & 15) == 0) && (((uintptr_t)o & 7) == 0)) {
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+        uint2* o4 = reinterpret_cast<uint2*>(o);
+        for (long long i = tid; i < (len >> 2); i += nthr) {
+            const float4 v = p4[i];
+            o4[i] = make_uint2(export_level(v.x) | (export_level(v.y) << 16),
+                               export_level(v.z) | (export_level(v.w) << 16));
+        }
+    } else {
+        for (long long i = tid; i < len; i += nthr) o[i] = (uint16_t)export_level(p[i]);
+    }
+}
+}  // namespace
+
+int export_u16_run(const float* in, uint16_t* out, const Dims& d, cudaStream_t stream) {
+    if (d.n_sel == 0) return MDIMG_OK;
+    MDIMG_LAUNCH k_export_u16<<<dim3(blocks_for(d.px(), 8), d.n_sel), NT, 0, stream>>>(in, out, d);
+    return check_launch("export_u16");
+}
+
 int clip01_run(const float* in, float* out, const Dims& d, cudaStream_t stream) {
     if (d.n_sel == 0) return MDIMG_OK;
     ClipF f;

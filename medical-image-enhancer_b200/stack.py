@@ -338,6 +338,18 @@ class StackOps:
         self._call(self.lib.mdimg_copy, self._ptr(src), self._ptr(dst), n, h, w, sp, ns, self._stream())
         return dst
 
+    def export_u16(self, src, dst=None, sel=None):
+        """uint16(clip(rint(x * 65535), 0, 65535)) of a float32 stack, as an int16-typed tensor holding
+        the uint16 bit pattern (torch has no arithmetic on uint16; view it with numpy)."""
+        n, h, w = self._img(src).shape
+        if dst is None:
+            dst = torch.empty((n, h, w), dtype=torch.int16, device=self.device)
+        if dst.dtype not in (torch.int16, torch.uint16) or tuple(dst.shape) != (n, h, w) or not dst.is_contiguous():
+            raise ValueError("export_u16: dst must be a contiguous [N, H, W] 16-bit tensor")
+        sp, ns = self._sel(sel)
+        self._call(self.lib.mdimg_export_u16, self._ptr(src), self._ptr(dst), n, h, w, sp, ns, self._stream())
+        return dst
+
 
 _ops_lock = threading.Lock()
 _ops_by_device: dict = {}

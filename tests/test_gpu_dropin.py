@@ -279,6 +279,38 @@ def test_empty_single_and_ragged_stacks(ops, synth):
             assert r.metrics_before(z)["entropy"] == pytest.approx(omet.compute_metrics(x)["entropy"], rel=1e-9)
 
 
+def test_uint16_export_is_img_as_uint_of_the_float_result(ops, synth):
+    """out_dtype=uint16: the host receives uint16(clip(rint(x * 65535), 0, 65535)) of exactly the float32
+    image the default path returns (bit for bit), hence within 1 LSB of the oracle's export wherever the
+    float images agree to 1 LSB."""
+    import torch
+    from mdimg_b200.batch import process_stack_host
+    raw = np.stack([synth.ct_slice(5000 + z, z / 4, size=128)[:, :126] for z in range(4)])      # 128 x 126: vector path
+    odd = np.stack([synth.ct_slice(5100 + z, z / 2, size=96)[:95, :93] for z in range(2)])      # odd sizes: scalar path
+    plan = synth.plan_full()
+    for stack in (raw, odd):
+        f32, res_f = process_stack_host(stack, plan, chunk=3, ops=ops)
+        f32 = f32.copy()
+        u16, res_u = process_stack_host(stack, plan, chunk=3, ops=ops, out_dtype=np.uint16)
+        assert u16.dtype == np.uint16 and u16.shape == stack.shape
+        want = np.clip(np.rint(f32 * np.float32(65535)), 0, 65535).astype(np.uint16)
+        np.testing.assert_array_equal(u16, want)
+        np.testing.assert_allclose(res_f.packed, res_u.packed, rtol=1e-9, atol=1e-12)
+        assert res_f.labels == res_u.labels
+        x = omet.normalize_image(stack[0])
+        ref, _ = oenh.apply_enhancements_from_params(x, plan)
+        ref16 = np.clip(np.rint(ref.astype(np.float32) * np.float32(65535)), 0, 65535).astype(np.int64)
+        assert float((np.abs(u16[0].astype(np.int64) - ref16) > 1).mean()) < 0.01
+    # edge values of the conversion itself: ties round to even, out-of-range clips
+    probe = np.array([[0.0, 1.0, 0.5, 1.5 / 65535, 2.5 / 65535, -0.25, 1.25, 0.999999]], np.float32)
+    t = torch.from_numpy(np.ascontiguousarray(np.tile(probe, (4, 1))[None])).to(ops.device)
+    got = ops.export_u16(t).cpu().numpy().view(np.uint16)[0, 0]
+    want = np.clip(np.rint(probe[0] * np.float32(65535)), 0, 65535).astype(np.uint16)
+    np.testing.assert_array_equal(got, want)
+    with pytest.raises(ValueError):
+        process_stack_host(raw, plan, ops=ops, out_dtype=np.int32)
+
+
 def test_score_plans_matches_the_tool_loop(ops, images, synth):
     """K candidate plans x N images (pipeline/tools.py:95-183 semantics) vs the oracle run one by one."""
     import torch

@@ -62,7 +62,8 @@ enum mdimg_op {
     MDIMG_OP_BILATERAL = 11,
     MDIMG_OP_TV = 12,        /* param = max_iter */
     MDIMG_OP_MINMAX = 13,
-    MDIMG_OP_VALIDATION = 14
+    MDIMG_OP_VALIDATION = 14,
+    MDIMG_OP_ENHANCE = 15    /* param = clahe kernel size (clamped plan value) */
 };
 
 const char* mdimg_last_error(void);
@@ -197,6 +198,63 @@ int mdimg_export_u16(const float* in, uint16_t* out, int n, int h, int w, const 
                      void* stream);
 int mdimg_copy(const float* in, float* out, int n, int h, int w, const int32_t* sel, int n_sel,
                void* stream);
+
+/* ---- the whole enhancement call ----------------------------------------------------------- */
+/* apply_enhancements_from_params(image, plan) (pipeline/enhancement.py:235-369) for every slice of a
+ * stack in ONE call: PARAM_BOUNDS clamping (pipeline/schemas.py:16-28), the seven gated steps in their
+ * fixed order, the final clip, and the three safeguards (halo re-run in the plan's own order with half
+ * the unsharp amount, corrective denoise, 40 % blend-back) with the reference's decisions taken per
+ * slice.  The host arithmetic between the kernels (which slices a safeguard fires on) runs inside the
+ * call, which therefore synchronises `stream` a few times. */
+enum mdimg_step {            /* index into the reference's fixed step order (enhancement.py:266-315) */
+    MDIMG_STEP_DENOISE = 0, MDIMG_STEP_CLAHE = 1, MDIMG_STEP_GAMMA = 2, MDIMG_STEP_UNSHARP = 3,
+    MDIMG_STEP_POST_DENOISE = 4, MDIMG_STEP_BILATERAL = 5, MDIMG_STEP_TV_DENOISE = 6
+};
+typedef struct mdimg_enhance_plan {
+    int32_t n_ops;               /* entries of ops[] */
+    int32_t ops[16];             /* plan.recommended_ops in the plan's order, as MDIMG_STEP_* (unknown names dropped) */
+    double clahe_clip_limit;     /* EnhancementParams (pipeline/schemas.py:36-100); clamped by mdimg_plan_clamp */
+    int32_t clahe_tile_size;
+    double gamma;
+    double unsharp_radius;
+    double unsharp_amount;
+    int32_t denoise_hard;        /* denoise_mode: 0 'soft' (also for unknown strings), 1 'hard' */
+    double post_denoise_strength;
+    int32_t bilateral_d;
+    double bilateral_sigma_color;
+    double bilateral_sigma_space;
+    double tv_denoise_weight;
+} mdimg_enhance_plan;
+/* Host tables that depend on the CLAMPED plan and the image size.  A Python caller fills them with
+ * numpy / scipy's own values (bit-for-bit the reference's); mdimg_enhance_tables_default computes them
+ * with the C library's exp (which may differ from numpy's in the last bit of a weight). */
+typedef struct mdimg_enhance_tables {
+    int32_t gauss_radius;        /* int(4 * unsharp_radius + 0.5) */
+    double gauss_taps[13];       /* scipy.ndimage _gaussian_kernel1d(unsharp_radius): centre, then +1 ... +radius */
+    int32_t bilateral_d_eff;     /* min(bilateral_d, 9), made odd (pipeline/enhancement.py:117-121); 0 = off */
+    double bilateral_spatial[81];/* exp(-(dx^2 + dy^2) / (2 sigma_space^2 d^2)), row-major dy, dx */
+    int32_t pct_lo[5], pct_hi[5];/* numpy percentile plan for h*w elements, q = 5, 25, 75, 95, 90 (see mdimg_metrics) */
+    float pct_gamma[5];
+} mdimg_enhance_tables;
+/* Result flags per slice. */
+#define MDIMG_FLAG_HALO 1            /* "[safeguard] Unsharp reduced to ..." */
+#define MDIMG_FLAG_NOISE_GUARD 2     /* "Auto-corrective denoise (noise guard)" */
+#define MDIMG_FLAG_OVER_PROCESSED 4  /* "Blend-back 40% original (over-processing guard)" */
+#define MDIMG_FLAG_ERR_CLAHE_RANGE 8 /* the reference raises ValueError("Images of type float must be between -1 and 1.") */
+#define MDIMG_FLAG_ERR_GAMMA_NEG 16  /* the reference raises ValueError("Image Correction methods work correctly only on ...") */
+
+/* Clamps every parameter to PARAM_BOUNDS in place (idempotent). */
+int mdimg_plan_clamp(mdimg_enhance_plan* plan);
+/* Fills `tables` for a clamped plan and h x w images with the C library's arithmetic. */
+int mdimg_enhance_tables_default(const mdimg_enhance_plan* plan, int h, int w, mdimg_enhance_tables* tables);
+/* in / out: device float32 [n][h][w] (out must not alias in).  plan, tables: host.  rows_before: device
+ * double[n][MDIMG_METRIC_COLS] rows of mdimg_metrics(in, flags = 1), or NULL (computed here).
+ * rows_after: device double[n][MDIMG_METRIC_COLS], receives mdimg_metrics(out, flags = 1), or NULL.
+ * flags_out: HOST int32[n] (MDIMG_FLAG_*); a slice with an error flag is returned unchanged.
+ * tv_iters_out: HOST int32[n] or NULL.  Workspace: MDIMG_OP_ENHANCE with param = clamped clahe_tile_size. */
+int mdimg_enhance(const float* in, float* out, int n, int h, int w, const mdimg_enhance_plan* plan,
+                  const mdimg_enhance_tables* tables, const double* rows_before, double* rows_after,
+                  int32_t* flags_out, int32_t* tv_iters_out, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

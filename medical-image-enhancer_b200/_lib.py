@@ -64,6 +64,35 @@ PROTOTYPES = {
     "mdimg_export_u16": (_i, [_p, _p, *_IMG, _p]),
 }
 
+
+
+class EnhancePlan(C.Structure):
+    """mdimg_enhance_plan (include/mdimg_b200.h)."""
+    _fields_ = [("n_ops", C.c_int32), ("ops", C.c_int32 * 16),
+                ("clahe_clip_limit", _d), ("clahe_tile_size", C.c_int32), ("gamma", _d),
+                ("unsharp_radius", _d), ("unsharp_amount", _d), ("denoise_hard", C.c_int32),
+                ("post_denoise_strength", _d), ("bilateral_d", C.c_int32),
+                ("bilateral_sigma_color", _d), ("bilateral_sigma_space", _d), ("tv_denoise_weight", _d)]
+
+
+class EnhanceTables(C.Structure):
+    """mdimg_enhance_tables (include/mdimg_b200.h)."""
+    _fields_ = [("gauss_radius", C.c_int32), ("gauss_taps", _d * 13),
+                ("bilateral_d_eff", C.c_int32), ("bilateral_spatial", _d * 81),
+                ("pct_lo", C.c_int32 * 5), ("pct_hi", C.c_int32 * 5), ("pct_gamma", C.c_float * 5)]
+
+
+STEP_NAMES = ("denoise", "clahe", "gamma", "unsharp", "post_denoise", "bilateral", "tv_denoise")
+FLAG_HALO, FLAG_NOISE_GUARD, FLAG_OVER_PROCESSED, FLAG_ERR_CLAHE_RANGE, FLAG_ERR_GAMMA_NEG = 1, 2, 4, 8, 16
+OP_ENHANCE = 15
+
+PROTOTYPES.update({
+    "mdimg_plan_clamp": (_i, [C.POINTER(EnhancePlan)]),
+    "mdimg_enhance_tables_default": (_i, [C.POINTER(EnhancePlan), _i, _i, C.POINTER(EnhanceTables)]),
+    "mdimg_enhance": (_i, [_p, _p, _i, _i, _i, C.POINTER(EnhancePlan), C.POINTER(EnhanceTables), _p, _p,
+                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), *_WS]),
+})
+
 _lock = threading.Lock()
 _lib = None
 _initialised_devices: set[int] = set()

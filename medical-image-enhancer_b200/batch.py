@@ -108,7 +108,7 @@ def process_chunk(ops: StackOps, raw: torch.Tensor, plan, keep_enhanced: bool = 
     n = raw.shape[0]
     x = ops.normalize(raw)
     rows_b = ops.metrics(x, with_niqe=True)
-    res = eng.enhance_from_params(x, plan, rows_before=rows_b, on_error="flag")
+    res = eng.enhance_plan(x, plan, rows_before=rows_b, on_error="flag")
     rows_a = res.rows_after
     fr = ops.fullref(x, res.image)
     packed = torch.empty((n, PACK_COLS), dtype=torch.float64, device=ops.device)

@@ -141,6 +141,7 @@ size_t mdimg_workspace_bytes(int op, int n, int h, int w, int param) {
             return a.off;
         }
         case MDIMG_OP_BILATERAL: return 0;
+        case MDIMG_OP_ENHANCE: return enhance_workspace_bytes(n, h, w, param);
         case MDIMG_OP_TV: return tv_workspace_bytes(n, n, h, w, param > 0 ? param : 200);
         default: return 0;
     }

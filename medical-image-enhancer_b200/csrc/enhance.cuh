@@ -71,4 +71,7 @@ size_t tv_workspace_bytes(int n, int n_sel, int h, int w, int max_iter);
 int tv_chambolle_run(const float* in, float* out, const Dims& d, double weight, double eps,
                      int max_iter, int* iters_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+// ---- engine.cu (mdimg_enhance) ---------------------------------------------------------------
+size_t enhance_workspace_bytes(int n, int h, int w, int clahe_kernel_size);
+
 }  // namespace mdimg

@@ -10,6 +10,7 @@ which only the flagged slices are re-processed (``sel`` lists, no pixel gathers)
 from __future__ import annotations
 
 import logging
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -372,6 +373,55 @@ class Engine:
             tv_iterations=None if tv_iters is None else tv_iters.cpu().numpy(),
             sigma_before=sigma_before, quality_before=quality_before, rows_after=rows,
         )
+
+    def enhance_plan(self, image: torch.Tensor, plan, *, rows_before: Optional[torch.Tensor] = None,
+                     on_error: str = "raise") -> EnhanceResult:
+        """`enhance_from_params_native` (one library call) unless MDIMG_NATIVE_ENGINE=0 selects the torch-side
+        control flow; the two are interchangeable (same pixels, flags, labels)."""
+        if os.environ.get("MDIMG_NATIVE_ENGINE", "1") != "0":
+            return self.enhance_from_params_native(image, plan, rows_before=rows_before, on_error=on_error)
+        return self.enhance_from_params(image, plan, rows_before=rows_before, on_error=on_error)
+
+    def enhance_from_params_native(self, image: torch.Tensor, plan, *, rows_before: Optional[torch.Tensor] = None,
+                                   on_error: str = "raise") -> EnhanceResult:
+        """The same call through `mdimg_enhance`: the control flow above runs in C++ inside the library
+        (one C-ABI call per stack, what a non-Python host binds); labels are rebuilt here from the
+        returned flags.  Results equal `enhance_from_params` (tests/test_gpu_dropin.py)."""
+        from . import _lib
+        out, rows_after, flags, iters, qc = self.ops.enhance(image, plan, rows_before=rows_before)
+        q = ClampedParams.from_params(plan.params)
+        plan_ops = [op.lower().strip() for op in plan.recommended_ops]
+        common = [self._label(nm, q) for nm in _STEP_ORDER if nm in plan_ops and self._enabled(nm, q)]
+        n = image.shape[0]
+        labels: List[List[str]] = []
+        errors: Dict[int, str] = {}
+        for i in range(n):
+            f = int(flags[i])
+            if f & (_lib.FLAG_ERR_CLAHE_RANGE | _lib.FLAG_ERR_GAMMA_NEG):
+                msg = ("Images of type float must be between -1 and 1." if f & _lib.FLAG_ERR_CLAHE_RANGE else
+                       "Image Correction methods work correctly only on images with non-negative values. "
+                       "Use skimage.exposure.rescale_intensity.")
+                if on_error == "raise":
+                    raise ValueError(msg)
+                errors[i] = msg
+                labels.append([f"ERROR: {msg}"])
+                continue
+            lab = list(common)
+            if f & _lib.FLAG_HALO:
+                lab.append(f"[safeguard] Unsharp reduced to {q.u_amount * 0.5:.2f}")
+            if f & _lib.FLAG_NOISE_GUARD:
+                lab.append("Auto-corrective denoise (noise guard)")
+            if f & _lib.FLAG_OVER_PROCESSED:
+                lab.append("Blend-back 40% original (over-processing guard)")
+            labels.append(lab)
+        for bit, msg in ((_lib.FLAG_HALO, HALO_MSG), (_lib.FLAG_NOISE_GUARD, NOISE_MSG), (_lib.FLAG_OVER_PROCESSED, OVER_MSG)):
+            if (flags & bit).any():
+                logger.warning(msg)                 # the reference logs these (pipeline/enhancement.py:320,357,363)
+        ran_tv = "tv_denoise" in plan_ops and self._enabled("tv_denoise", q)
+        return EnhanceResult(image=out, labels=labels, halo=(flags & _lib.FLAG_HALO) != 0,
+                             noise_guard=(flags & _lib.FLAG_NOISE_GUARD) != 0,
+                             over_processed=(flags & _lib.FLAG_OVER_PROCESSED) != 0, errors=errors,
+                             tv_iterations=iters.copy() if ran_tv else None, rows_after=rows_after)
 
     # ---- apply_enhancements (issue-gated defaults) ------------------------------------------------
     def enhance_from_issues(self, image: torch.Tensor, issues: Sequence[str], *,

@@ -77,5 +77,5 @@ def apply_enhancements(image: np.ndarray, issues: List[str]) -> Tuple[np.ndarray
 def apply_enhancements_from_params(image: np.ndarray, plan: "EnhancementPlan") -> Tuple[np.ndarray, List[str]]:
     """Plan-driven enhancement with PARAM_BOUNDS clamping and safeguards (pipeline/enhancement.py:235-369)."""
     ops = get_ops()
-    res = Engine(ops).enhance_from_params(_to_stack(image, ops), plan)
+    res = Engine(ops).enhance_plan(_to_stack(image, ops), plan)
     return res.image[0].cpu().numpy(), res.labels[0]

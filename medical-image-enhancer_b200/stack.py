@@ -338,6 +338,60 @@ class StackOps:
         self._call(self.lib.mdimg_copy, self._ptr(src), self._ptr(dst), n, h, w, sp, ns, self._stream())
         return dst
 
+    def enhance(self, image: torch.Tensor, plan, rows_before: Optional[torch.Tensor] = None):
+        """apply_enhancements_from_params for a whole stack in ONE library call (`mdimg_enhance`: clamping,
+        step gating, safeguards and their per-slice decisions run in C++).  `plan` has `recommended_ops`
+        and `params` like the reference's EnhancementPlan.  Returns (enhanced [N, H, W] float32,
+        rows_after [N, 24] float64 device, flags int32 numpy [N], tv_iterations int32 numpy [N],
+        clamped plan struct)."""
+        n, h, w = self._img(image).shape
+        q = _lib.EnhancePlan()
+        names = [op.lower().strip() for op in plan.recommended_ops]
+        steps = [_lib.STEP_NAMES.index(nm) for nm in names if nm in _lib.STEP_NAMES][:16]
+        q.n_ops = len(steps)
+        for i, st in enumerate(steps):
+            q.ops[i] = st
+        p = plan.params
+        q.clahe_clip_limit = float(p.clahe_clip_limit)
+        # int() of the clamped value, as the reference does (pipeline/enhancement.py:250)
+        q.clahe_tile_size = int(max(4, min(48, p.clahe_tile_size)))
+        q.gamma = float(p.gamma)
+        q.unsharp_radius = float(p.unsharp_radius)
+        q.unsharp_amount = float(p.unsharp_amount)
+        q.denoise_hard = 1 if p.denoise_mode == "hard" else 0
+        q.post_denoise_strength = float(p.post_denoise_strength)
+        q.bilateral_d = int(max(0, min(13, p.bilateral_d)))
+        q.bilateral_sigma_color = float(p.bilateral_sigma_color)
+        q.bilateral_sigma_space = float(p.bilateral_sigma_space)
+        q.tv_denoise_weight = float(p.tv_denoise_weight)
+        check(self.lib.mdimg_plan_clamp(C.byref(q)))
+        # tables from numpy / scipy's own arithmetic (bit-for-bit the reference's weights)
+        t = _lib.EnhanceTables()
+        taps = gaussian_taps(q.unsharp_radius)
+        t.gauss_radius = len(taps) - 1
+        for i, v in enumerate(taps):
+            t.gauss_taps[i] = float(v)
+        if q.bilateral_d > 0:
+            deff, spatial = bilateral_spatial(q.bilateral_d, q.bilateral_sigma_space)
+            t.bilateral_d_eff = deff
+            for i, v in enumerate(spatial.ravel()):
+                t.bilateral_spatial[i] = float(v)
+        lo, hi, gamma = percentile_plan(h * w)
+        for i in range(5):
+            t.pct_lo[i], t.pct_hi[i], t.pct_gamma[i] = int(lo[i]), int(hi[i]), float(gamma[i])
+        out = torch.empty_like(image)
+        rows_after = torch.full((n, _lib.METRIC_COLS), float("nan"), dtype=torch.float64, device=self.device)
+        flags = np.zeros(n, np.int32)
+        iters = np.zeros(n, np.int32)
+        if rows_before is not None and (rows_before.dtype != torch.float64 or tuple(rows_before.shape) != (n, _lib.METRIC_COLS)
+                                        or not rows_before.is_contiguous()):
+            raise ValueError("rows_before must be a contiguous [N, 24] float64 tensor")
+        ws, wsb = self._ws_for(_lib.OP_ENHANCE, n, h, w, int(q.clahe_tile_size))
+        self._call(self.lib.mdimg_enhance, self._ptr(image), self._ptr(out), n, h, w, C.byref(q), C.byref(t),
+                   self._ptr(rows_before), self._ptr(rows_after), flags.ctypes.data_as(C.POINTER(C.c_int32)),
+                   iters.ctypes.data_as(C.POINTER(C.c_int32)), ws, wsb, self._stream())
+        return out, rows_after, flags, iters, q
+
     def export_u16(self, src, dst=None, sel=None):
         """uint16(clip(rint(x * 65535), 0, 65535)) of a float32 stack, as an int16-typed tensor holding
         the uint16 bit pattern (torch has no arithmetic on uint16; view it with numpy)."""

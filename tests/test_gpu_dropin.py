@@ -311,6 +311,72 @@ def test_uint16_export_is_img_as_uint_of_the_float_result(ops, synth):
         process_stack_host(raw, plan, ops=ops, out_dtype=np.int32)
 
 
+def test_native_enhance_call_equals_the_python_engine(ops, synth):
+    """mdimg_enhance (the whole apply_enhancements_from_params control flow in C++, one C-ABI call per stack)
+    against Engine.enhance_from_params (the same logic on torch tensors, itself checked against the oracle):
+    pixels bit-equal, flags / labels / TV iteration counts equal, metric rows equal to accumulation order."""
+    import torch
+    from mdimg_b200.engine import Engine
+    from mdimg_b200.pipeline.schemas import EnhancementParams, EnhancementPlan
+    eng = Engine(ops)
+    rng = np.random.default_rng(5)
+    ims = [synth.fixture_clean(), synth.fixture_noisy(), synth.fixture_low_contrast(),
+           rng.random((64, 64), dtype=np.float32),                                   # noise: guards fire
+           np.clip(synth.fixture_clean() * 1.6 - 0.2, 0, 1).astype(np.float32)]
+    stack = torch.from_numpy(np.stack(ims)).to(ops.device)
+    plans = [
+        synth.plan_full(),
+        synth.plan_cr() if hasattr(synth, "plan_cr") else EnhancementPlan(
+            recommended_ops=["clahe", "unsharp"], params=EnhancementParams(clahe_clip_limit=0.03, clahe_tile_size=32,
+                                                                           unsharp_radius=2.0, unsharp_amount=1.5)),
+        EnhancementPlan(recommended_ops=["denoise", "gamma", "unsharp"],                  # out-of-bounds values: clamping
+                        params=EnhancementParams(denoise_mode="hard", gamma=1.9, unsharp_radius=5.0, unsharp_amount=9.0,
+                                                 clahe_clip_limit=0.5, clahe_tile_size=100, post_denoise_strength=0.0)),
+        EnhancementPlan(recommended_ops=["Unsharp ", "gamma", "CLAHE", "tv_denoise", "nonsense"],   # plan order != step order
+                        params=EnhancementParams(clahe_clip_limit=0.01, clahe_tile_size=8, gamma=1.05, unsharp_radius=1.0,
+                                                 unsharp_amount=2.0, tv_denoise_weight=0.02)),
+        EnhancementPlan(recommended_ops=["unsharp"], params=EnhancementParams(unsharp_radius=1.5, unsharp_amount=2.5)),
+        EnhancementPlan(recommended_ops=["bilateral", "post_denoise"],
+                        params=EnhancementParams(bilateral_d=6, bilateral_sigma_color=0.1, bilateral_sigma_space=0.1,
+                                                 post_denoise_strength=0.6)),
+        EnhancementPlan(recommended_ops=[], params=EnhancementParams()),
+    ]
+    fired = set()
+    for plan in plans:
+        ref = eng.enhance_from_params(stack, plan, on_error="flag")
+        got = eng.enhance_from_params_native(stack, plan, on_error="flag")
+        np.testing.assert_array_equal(got.image.cpu().numpy(), ref.image.cpu().numpy())
+        assert got.labels == ref.labels
+        np.testing.assert_array_equal(got.halo, ref.halo)
+        np.testing.assert_array_equal(got.noise_guard, ref.noise_guard)
+        np.testing.assert_array_equal(got.over_processed, ref.over_processed)
+        if ref.tv_iterations is None:
+            assert got.tv_iterations is None
+        else:
+            np.testing.assert_array_equal(got.tv_iterations, ref.tv_iterations)
+        np.testing.assert_allclose(got.rows_after.cpu().numpy(), ref.rows_after.cpu().numpy(), rtol=1e-9, atol=1e-12,
+                                   equal_nan=True)
+        fired |= {k for k, v in (("halo", ref.halo), ("noise", ref.noise_guard), ("over", ref.over_processed)) if v.any()}
+        # with the caller's rows of the input
+        rows_b = ops.metrics(stack, with_niqe=True)
+        again = eng.enhance_from_params_native(stack, plan, rows_before=rows_b, on_error="flag")
+        np.testing.assert_array_equal(again.image.cpu().numpy(), ref.image.cpu().numpy())
+    assert fired == {"halo", "noise", "over"}, fired           # every safeguard path was exercised
+    # the reference's data-dependent ValueErrors: gamma on negative pixels, CLAHE outside [-1, 1]
+    bad = stack.clone()
+    bad[1] = bad[1] - 0.5
+    bad[3] = bad[3] * 3.0
+    for plan in (EnhancementPlan(recommended_ops=["gamma"], params=EnhancementParams(gamma=0.8)),
+                 EnhancementPlan(recommended_ops=["clahe"], params=EnhancementParams())):
+        ref = eng.enhance_from_params(bad, plan, on_error="flag")
+        got = eng.enhance_from_params_native(bad, plan, on_error="flag")
+        assert got.errors == ref.errors and got.errors
+        assert got.labels == ref.labels
+        np.testing.assert_array_equal(got.image.cpu().numpy(), ref.image.cpu().numpy())
+        with pytest.raises(ValueError):
+            eng.enhance_from_params_native(bad, plan)
+
+
 def test_score_plans_matches_the_tool_loop(ops, images, synth):
     """K candidate plans x N images (pipeline/tools.py:95-183 semantics) vs the oracle run one by one."""
     import torch

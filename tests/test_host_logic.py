@@ -185,3 +185,70 @@ def test_tapered_schedule_covers_the_stack():
             assert sum(s) == n and all(c > 0 for c in s)
             assert s == sorted(s, reverse=True) or s[-1] >= s[-2] or len(s) < 3   # non-increasing but for the remainder
     assert tapered_schedule(1024, 4)[:4] == [160, 160, 160, 160]
+
+
+# ---- host-side entry points of the library (no device work: run on the CPU-only box) -----------
+def _c_plan(**kw):
+    from mdimg_b200 import _lib
+    q = _lib.EnhancePlan()
+    vals = dict(clahe_clip_limit=0.015, clahe_tile_size=16, gamma=1.0, unsharp_radius=0.8, unsharp_amount=0.5,
+                denoise_hard=0, post_denoise_strength=0.3, bilateral_d=0, bilateral_sigma_color=0.05,
+                bilateral_sigma_space=0.05, tv_denoise_weight=0.0)
+    vals.update(kw)
+    for k, v in vals.items():
+        setattr(q, k, v)
+    return q
+
+
+def test_plan_clamp_is_param_bounds():
+    """mdimg_plan_clamp == the reference's max(lo, min(hi, v)) over PARAM_BOUNDS (pipeline/schemas.py:16-28)."""
+    import ctypes as C
+
+    from mdimg_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(11)
+    names = ["clahe_clip_limit", "clahe_tile_size", "gamma", "unsharp_radius", "unsharp_amount",
+             "post_denoise_strength", "bilateral_d", "bilateral_sigma_color", "bilateral_sigma_space", "tv_denoise_weight"]
+    for _ in range(200):
+        raw = {}
+        for nm in names:
+            lo, hi = engine.PARAM_BOUNDS[nm]
+            v = rng.uniform(lo - (hi - lo), hi + (hi - lo))
+            raw[nm] = int(round(v)) if nm in ("clahe_tile_size", "bilateral_d") else float(v)
+        q = _c_plan(**raw)
+        assert lib.mdimg_plan_clamp(C.byref(q)) == 0
+        want = engine.ClampedParams.from_params(SimpleNamespace(denoise_mode="soft", **raw))
+        assert q.clahe_clip_limit == want.clip_limit and q.clahe_tile_size == want.tile_size and q.gamma == want.gamma
+        assert q.unsharp_radius == want.u_radius and q.unsharp_amount == want.u_amount
+        assert q.post_denoise_strength == want.post_str and q.bilateral_d == want.bilateral_d
+        assert q.bilateral_sigma_color == want.bilateral_sc and q.bilateral_sigma_space == want.bilateral_ss
+        assert q.tv_denoise_weight == want.tv_weight
+        before = bytes(q)
+        lib.mdimg_plan_clamp(C.byref(q))
+        assert bytes(q) == before                               # idempotent
+
+
+def test_default_tables_follow_numpy_and_scipy():
+    """mdimg_enhance_tables_default: the percentile plan equals numpy's float32 plan exactly; the Gaussian
+    taps and bilateral weights equal numpy's to the last bit or the one before (C exp vs numpy's exp)."""
+    import ctypes as C
+
+    from mdimg_b200 import _lib
+    lib = _lib.load_library()
+    for (h, w) in [(64, 64), (512, 512), (94, 141), (3000, 3000), (4096, 4096), (7, 9)]:
+        for sigma, d, ss in [(0.8, 5, 0.05), (0.2, 0, 0.1), (3.0, 13, 0.2), (2.0, 8, 0.005), (1.37, 1, 0.07)]:
+            q = _c_plan(unsharp_radius=sigma, bilateral_d=d, bilateral_sigma_space=ss)
+            t = _lib.EnhanceTables()
+            assert lib.mdimg_enhance_tables_default(C.byref(q), h, w, C.byref(t)) == 0
+            lo, hi, g = percentile_plan(h * w)
+            assert list(t.pct_lo) == [int(v) for v in lo] and list(t.pct_hi) == [int(v) for v in hi]
+            assert [np.float32(v) for v in t.pct_gamma] == [np.float32(v) for v in g]
+            taps = gaussian_taps(sigma)
+            assert t.gauss_radius == len(taps) - 1
+            np.testing.assert_allclose(np.array(t.gauss_taps[:len(taps)]), taps, rtol=2.3e-16, atol=0)
+            if d > 0:
+                deff, spatial = bilateral_spatial(d, ss)
+                assert t.bilateral_d_eff == deff
+                np.testing.assert_allclose(np.array(t.bilateral_spatial[:deff * deff]), spatial.ravel(), rtol=2.3e-16, atol=0)
+            else:
+                assert t.bilateral_d_eff == 0

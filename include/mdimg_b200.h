@@ -256,6 +256,22 @@ int mdimg_enhance(const float* in, float* out, int n, int h, int w, const mdimg_
                   const mdimg_enhance_tables* tables, const double* rows_before, double* rows_after,
                   int32_t* flags_out, int32_t* tv_iters_out, void* ws, size_t ws_bytes, void* stream);
 
+/* apply_enhancements(image, issues) (pipeline/enhancement.py:151-227): the issue-gated chain with the fixed
+ * ENHANCEMENT_PARAMS (enhancement.py:32-42) -- noise -> wavelet denoise; low_contrast / clipping -> CLAHE;
+ * one-sided clipping -> gamma 0.95 / 1.05; blur -> unsharp + light denoise -- the final clip and the
+ * noise-amplification guard.  issues: OR of MDIMG_ISSUE_*.  tables: gauss_taps / gauss_radius for
+ * unsharp_radius = 0.8 (mdimg_enhance_tables_default on a default plan).  sigma_before: device double[n]
+ * estimate_sigma of the input, or NULL.  flags_out: HOST int32[n] (MDIMG_FLAG_NOISE_GUARD, MDIMG_FLAG_ERR_*).
+ * Workspace: MDIMG_OP_ENHANCE with param = 16. */
+#define MDIMG_ISSUE_NOISE 1
+#define MDIMG_ISSUE_BLUR 2
+#define MDIMG_ISSUE_LOW_CONTRAST 4
+#define MDIMG_ISSUE_CLIPPING_LOW 8
+#define MDIMG_ISSUE_CLIPPING_HIGH 16
+int mdimg_enhance_issues(const float* in, float* out, int n, int h, int w, int issues,
+                         const mdimg_enhance_tables* tables, const double* sigma_before, int32_t* flags_out,
+                         void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

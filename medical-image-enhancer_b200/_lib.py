@@ -85,12 +85,14 @@ class EnhanceTables(C.Structure):
 STEP_NAMES = ("denoise", "clahe", "gamma", "unsharp", "post_denoise", "bilateral", "tv_denoise")
 FLAG_HALO, FLAG_NOISE_GUARD, FLAG_OVER_PROCESSED, FLAG_ERR_CLAHE_RANGE, FLAG_ERR_GAMMA_NEG = 1, 2, 4, 8, 16
 OP_ENHANCE = 15
+ISSUE_BITS = {"noise": 1, "blur": 2, "low_contrast": 4, "clipping_low": 8, "clipping_high": 16}
 
 PROTOTYPES.update({
     "mdimg_plan_clamp": (_i, [C.POINTER(EnhancePlan)]),
     "mdimg_enhance_tables_default": (_i, [C.POINTER(EnhancePlan), _i, _i, C.POINTER(EnhanceTables)]),
     "mdimg_enhance": (_i, [_p, _p, _i, _i, _i, C.POINTER(EnhancePlan), C.POINTER(EnhanceTables), _p, _p,
                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), *_WS]),
+    "mdimg_enhance_issues": (_i, [_p, _p, _i, _i, _i, _i, C.POINTER(EnhanceTables), _p, C.POINTER(C.c_int32), *_WS]),
 })
 
 _lock = threading.Lock()

@@ -455,4 +455,88 @@ int mdimg_enhance(const float* in, float* out, int n, int h, int w, const mdimg_
     return check_launch("enhance");
 }
 
+int mdimg_enhance_issues(const float* in, float* out, int n, int h, int w, int issues,
+                         const mdimg_enhance_tables* tables, const double* sigma_before, int32_t* flags_out,
+                         void* ws, size_t ws_bytes, void* stream) {
+    if (n < 0 || h < 1 || w < 1 || !in || !out || !tables || !flags_out || in == out)
+        return set_error(MDIMG_ERR_INVALID, "enhance_issues: bad arguments");
+    if (n == 0) return MDIMG_OK;
+    // ENHANCEMENT_PARAMS (pipeline/enhancement.py:32-42)
+    Ctx c;
+    c.n = n; c.h = h; c.w = w; c.in = in; c.t = tables; c.stream = stream;
+    std::memset(&c.q, 0, sizeof(c.q));
+    c.q.clahe_clip_limit = 0.015; c.q.clahe_tile_size = 16; c.q.unsharp_radius = 0.8; c.q.unsharp_amount = 0.5;
+    c.q.denoise_hard = 0; c.q.post_denoise_strength = 0.3;
+    Arena a(ws, ws_bytes);
+    carve(a, n, h, w, c.q.clahe_tile_size, c.b);
+    if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "enhance_issues: workspace too small (%zu > %zu)", a.off, ws_bytes);
+    cudaStream_t st_ = (cudaStream_t)stream;
+    const size_t img_bytes = sizeof(float) * (size_t)n * h * w;
+    float* cur = out;
+    float* tmp = c.b.tmp;
+    cudaMemcpyAsync(cur, in, img_bytes, cudaMemcpyDeviceToDevice, st_);
+    Pass p;
+    int rc = MDIMG_OK;
+    auto has = [&](int bit) { return (issues & bit) != 0; };
+    if (has(MDIMG_ISSUE_NOISE)) {
+        rc = apply_step(c, MDIMG_STEP_DENOISE, 0.0, cur, tmp, nullptr, 0, p, c.b.iters);
+        if (rc) return rc;
+    }
+    if (has(MDIMG_ISSUE_LOW_CONTRAST) || has(MDIMG_ISSUE_CLIPPING_LOW) || has(MDIMG_ISSUE_CLIPPING_HIGH)) {
+        rc = apply_step(c, MDIMG_STEP_CLAHE, 0.0, cur, tmp, nullptr, 0, p, c.b.iters);
+        if (rc) return rc;
+    }
+    double g = 0.0;
+    if (has(MDIMG_ISSUE_CLIPPING_LOW) && !has(MDIMG_ISSUE_CLIPPING_HIGH)) g = 0.95;          // gamma_brighten
+    else if (has(MDIMG_ISSUE_CLIPPING_HIGH) && !has(MDIMG_ISSUE_CLIPPING_LOW)) g = 1.05;     // gamma_darken
+    if (g != 0.0) {
+        c.q.gamma = g;
+        rc = apply_step(c, MDIMG_STEP_GAMMA, 0.0, cur, tmp, nullptr, 0, p, c.b.iters);
+        if (rc) return rc;
+    }
+    if (has(MDIMG_ISSUE_BLUR)) {
+        rc = apply_step(c, MDIMG_STEP_UNSHARP, c.q.unsharp_amount, cur, tmp, nullptr, 0, p, c.b.iters);
+        if (rc) return rc;
+        rc = apply_step(c, MDIMG_STEP_POST_DENOISE, 0.0, cur, tmp, nullptr, 0, p, c.b.iters);
+        if (rc) return rc;
+    }
+    rc = mdimg_clip01(cur, cur, n, h, w, nullptr, 0, stream);
+    if (rc) return rc;
+    std::vector<int32_t> err(n, 0);
+    rc = flush_checks(c, p, err);
+    if (rc) return rc;
+
+    // _check_noise_amplification + corrective light denoise (enhancement.py:55-63,221-225)
+    std::vector<double> s0(n), s1(n);
+    const double* sb = sigma_before;
+    if (!sb) {
+        rc = mdimg_estimate_sigma(in, n, h, w, nullptr, 0, c.b.quality, c.b.sub, c.b.sub_bytes, stream);
+        if (rc) return rc;
+        sb = c.b.quality;
+    }
+    rc = c.fetch(s0.data(), sb, sizeof(double) * n);
+    if (rc) return rc;
+    rc = mdimg_estimate_sigma(cur, n, h, w, nullptr, 0, c.b.sigma, c.b.sub, c.b.sub_bytes, stream);
+    if (rc) return rc;
+    rc = c.fetch(s1.data(), c.b.sigma, sizeof(double) * n);
+    if (rc) return rc;
+    std::vector<char> noise(n, 0), bad(n, 0);
+    for (int i = 0; i < n; ++i) noise[i] = !(s0[i] < 1e-8) && (s1[i] > s0[i] * 1.3);
+    int ns = c.select(noise);
+    if (ns > 0) {
+        rc = mdimg_light_denoise(cur, cur, n, h, w, c.b.sel, ns, 0.4, c.b.skipped, c.b.sub, c.b.sub_bytes, stream);
+        if (rc) return rc;
+        rc = mdimg_clip01(cur, cur, n, h, w, c.b.sel, ns, stream);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < n; ++i) bad[i] = err[i] != 0;
+    ns = c.select(bad);
+    if (ns > 0) { rc = mdimg_copy(in, cur, n, h, w, c.b.sel, ns, stream); if (rc) return rc; }
+    if (cur != out) cudaMemcpyAsync(out, cur, img_bytes, cudaMemcpyDeviceToDevice, st_);
+    for (int i = 0; i < n; ++i) flags_out[i] = (noise[i] ? MDIMG_FLAG_NOISE_GUARD : 0) | err[i];
+    cudaError_t e = cudaStreamSynchronize(st_);
+    if (e != cudaSuccess) return set_error(MDIMG_ERR_CUDA, "enhance_issues: %s", cudaGetErrorString(e));
+    return check_launch("enhance_issues");
+}
+
 }  // extern "C"

@@ -423,6 +423,43 @@ class Engine:
                              over_processed=(flags & _lib.FLAG_OVER_PROCESSED) != 0, errors=errors,
                              tv_iterations=iters.copy() if ran_tv else None, rows_after=rows_after)
 
+    def enhance_issues(self, image: torch.Tensor, issues: Sequence[str], *,
+                       sigma_before: Optional[torch.Tensor] = None) -> EnhanceResult:
+        """apply_enhancements through `mdimg_enhance_issues` (one library call; MDIMG_NATIVE_ENGINE=0 selects
+        `enhance_from_issues`, the same flow on torch tensors).  Raises the reference's ValueError when a
+        slice would have raised it."""
+        if os.environ.get("MDIMG_NATIVE_ENGINE", "1") == "0":
+            return self.enhance_from_issues(image, issues, sigma_before=sigma_before)
+        out, flags = self.ops.enhance_issues(image, issues, sigma_before=sigma_before)
+        if (flags & _lib.FLAG_ERR_CLAHE_RANGE).any():
+            raise ValueError("Images of type float must be between -1 and 1.")
+        if (flags & _lib.FLAG_ERR_GAMMA_NEG).any():
+            raise ValueError("Image Correction methods work correctly only on images with "
+                             "non-negative values. Use skimage.exposure.rescale_intensity.")
+        P = ENHANCEMENT_PARAMS
+        has = set(issues).__contains__
+        common: List[str] = []
+        if has("noise"):
+            common.append("Wavelet denoise (pre)")
+        if has("low_contrast") or has("clipping_low") or has("clipping_high"):
+            common.append(f"CLAHE (clip={P['clahe_clip_limit']}, tile={P['clahe_tile_size']})")
+        if has("clipping_low") and not has("clipping_high"):
+            common.append(f"Gamma brighten ({P['gamma_brighten']})")
+        elif has("clipping_high") and not has("clipping_low"):
+            common.append(f"Gamma darken ({P['gamma_darken']})")
+        if has("blur"):
+            common.append(f"Unsharp mask (r={P['unsharp_radius']}, a={P['unsharp_amount']})")
+            if P["post_denoise_strength"] > 0:
+                common.append(f"Light denoise (post, s={P['post_denoise_strength']})")
+        noise = (flags & _lib.FLAG_NOISE_GUARD) != 0
+        if noise.any():
+            logger.warning(NOISE_MSG)
+        labels = [list(common) + (["Auto-corrective denoise (noise guard)"] if noise[i] else [])
+                  for i in range(image.shape[0])]
+        n = image.shape[0]
+        return EnhanceResult(image=out, labels=labels, noise_guard=noise, halo=np.zeros(n, bool),
+                             over_processed=np.zeros(n, bool))
+
     # ---- apply_enhancements (issue-gated defaults) ------------------------------------------------
     def enhance_from_issues(self, image: torch.Tensor, issues: Sequence[str], *,
                             sigma_before: Optional[torch.Tensor] = None) -> EnhanceResult:

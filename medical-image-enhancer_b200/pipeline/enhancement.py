@@ -70,7 +70,7 @@ def _bilateral_filter(image: np.ndarray, d: int = 5, sigma_color: float = 0.05,
 def apply_enhancements(image: np.ndarray, issues: List[str]) -> Tuple[np.ndarray, List[str]]:
     """Issue-gated conservative enhancement (pipeline/enhancement.py:151-227)."""
     ops = get_ops()
-    res = Engine(ops).enhance_from_issues(_to_stack(image, ops), list(issues))
+    res = Engine(ops).enhance_issues(_to_stack(image, ops), list(issues))
     return res.image[0].cpu().numpy(), res.labels[0]
 
 

@@ -392,6 +392,28 @@ class StackOps:
                    iters.ctypes.data_as(C.POINTER(C.c_int32)), ws, wsb, self._stream())
         return out, rows_after, flags, iters, q
 
+    def enhance_issues(self, image: torch.Tensor, issues, sigma_before: Optional[torch.Tensor] = None):
+        """apply_enhancements(image, issues) for a whole stack in one library call (`mdimg_enhance_issues`).
+        Returns (enhanced [N, H, W] float32, flags int32 numpy [N])."""
+        n, h, w = self._img(image).shape
+        mask = 0
+        for name in issues:
+            mask |= _lib.ISSUE_BITS.get(name, 0)
+        t = _lib.EnhanceTables()
+        taps = gaussian_taps(0.8)                   # ENHANCEMENT_PARAMS["unsharp_radius"], scipy's own weights
+        t.gauss_radius = len(taps) - 1
+        for i, v in enumerate(taps):
+            t.gauss_taps[i] = float(v)
+        out = torch.empty_like(image)
+        flags = np.zeros(n, np.int32)
+        if sigma_before is not None and (sigma_before.dtype != torch.float64 or tuple(sigma_before.shape) != (n,)
+                                         or not sigma_before.is_contiguous()):
+            raise ValueError("sigma_before must be a contiguous [N] float64 tensor")
+        ws, wsb = self._ws_for(_lib.OP_ENHANCE, n, h, w, 16)
+        self._call(self.lib.mdimg_enhance_issues, self._ptr(image), self._ptr(out), n, h, w, int(mask), C.byref(t),
+                   self._ptr(sigma_before), flags.ctypes.data_as(C.POINTER(C.c_int32)), ws, wsb, self._stream())
+        return out, flags
+
     def export_u16(self, src, dst=None, sel=None):
         """uint16(clip(rint(x * 65535), 0, 65535)) of a float32 stack, as an int16-typed tensor holding
         the uint16 bit pattern (torch has no arithmetic on uint16; view it with numpy)."""

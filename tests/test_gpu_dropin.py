@@ -377,6 +377,35 @@ def test_native_enhance_call_equals_the_python_engine(ops, synth):
             eng.enhance_from_params_native(bad, plan)
 
 
+def test_native_issue_chain_equals_the_python_engine(ops, synth):
+    """mdimg_enhance_issues (apply_enhancements in one C-ABI call) against Engine.enhance_from_issues."""
+    import torch
+    from mdimg_b200.engine import Engine
+    eng = Engine(ops)
+    rng = np.random.default_rng(9)
+    ims = [synth.fixture_clean(), synth.fixture_noisy(), synth.fixture_low_contrast(),
+           np.clip(synth.fixture_clean() + 0.02 * rng.standard_normal((64, 64)), 0, 1).astype(np.float32)]
+    stack = torch.from_numpy(np.stack(ims)).to(ops.device)
+    guard = False
+    for issues in (["noise"], ["blur"], ["noise", "blur"], ["low_contrast", "clipping_low"], ["clipping_high", "blur"],
+                   ["clipping_low", "clipping_high"], ["noise", "blur", "low_contrast", "clipping_low"], [], ["unknown"]):
+        ref = eng.enhance_from_issues(stack, issues)
+        got = eng.enhance_issues(stack, issues)
+        np.testing.assert_array_equal(got.image.cpu().numpy(), ref.image.cpu().numpy())
+        assert got.labels == ref.labels
+        np.testing.assert_array_equal(got.noise_guard, ref.noise_guard)
+        guard |= bool(ref.noise_guard.any())
+        s0 = ops.estimate_sigma(stack)
+        again = eng.enhance_issues(stack, issues, sigma_before=s0)
+        np.testing.assert_array_equal(again.image.cpu().numpy(), ref.image.cpu().numpy())
+    assert guard                                                    # the noise guard fired somewhere
+    bad = stack.clone()
+    bad[2] = bad[2] * 3.0                                           # CLAHE input outside [-1, 1]
+    for fn in (eng.enhance_issues, eng.enhance_from_issues):
+        with pytest.raises(ValueError, match="between -1 and 1"):
+            fn(bad, ["low_contrast"])
+
+
 def test_score_plans_matches_the_tool_loop(ops, images, synth):
     """K candidate plans x N images (pipeline/tools.py:95-183 semantics) vs the oracle run one by one."""
     import torch

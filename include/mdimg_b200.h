@@ -272,6 +272,28 @@ int mdimg_enhance_issues(const float* in, float* out, int n, int h, int w, int i
                          const mdimg_enhance_tables* tables, const double* sigma_before, int32_t* flags_out,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* ---- host scalar logic of the path (no device work) -------------------------------------------- */
+/* detect_issues (pipeline/metrics.py:166-179) on one HOST metrics row: OR of MDIMG_ISSUE_* in the reference's
+ * order noise, blur, low_contrast, clipping_low, clipping_high (THRESHOLDS, metrics.py:25-34). */
+int mdimg_detect_issues(const double* metrics_row);
+/* The scalar part of compute_validation (pipeline/metrics.py:237-329) from one HOST row of mdimg_validation:
+ * gains, quality_improvement, threshold tests and the pass rule, in the reference's python-float arithmetic. */
+typedef struct mdimg_validation_scalars {
+    double ssim, psnr, quality_improvement;
+    int32_t meets_ssim, meets_psnr, meets_improvement, passes;
+    double niqe_before, niqe_after;
+    int32_t niqe_improved;
+    double contrast_gain, sharpness_gain, noise_change;
+    double entropy_change, snr_change, cnr_change, edge_density_change, histogram_spread_change;
+    double edge_ratio, local_contrast_change, gradient_strength_change, gradient_entropy_change;
+} mdimg_validation_scalars;
+int mdimg_validation_scalars_of(const double* validation_row, mdimg_validation_scalars* out);
+/* compute_objective_score (pipeline/metrics.py:337-408): the score BEFORE its round(., 4) and the eleven
+ * penalty / reward parts in the order of the reference's breakdown dict (contrast_gain, sharpness_gain,
+ * noise_penalty, niqe_degradation, halo_penalty, entropy_penalty, snr_reward, hs_reward,
+ * local_contrast_reward, gradient_strength_reward, gradient_entropy_penalty), also unrounded. */
+int mdimg_objective_score(const mdimg_validation_scalars* v, double* score, double parts[11]);
+
 #ifdef __cplusplus
 }
 #endif

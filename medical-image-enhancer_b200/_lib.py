@@ -82,6 +82,17 @@ class EnhanceTables(C.Structure):
                 ("pct_lo", C.c_int32 * 5), ("pct_hi", C.c_int32 * 5), ("pct_gamma", C.c_float * 5)]
 
 
+class ValidationScalars(C.Structure):
+    """mdimg_validation_scalars (include/mdimg_b200.h)."""
+    _fields_ = [("ssim", _d), ("psnr", _d), ("quality_improvement", _d),
+                ("meets_ssim", C.c_int32), ("meets_psnr", C.c_int32), ("meets_improvement", C.c_int32), ("passes", C.c_int32),
+                ("niqe_before", _d), ("niqe_after", _d), ("niqe_improved", C.c_int32),
+                ("contrast_gain", _d), ("sharpness_gain", _d), ("noise_change", _d),
+                ("entropy_change", _d), ("snr_change", _d), ("cnr_change", _d), ("edge_density_change", _d),
+                ("histogram_spread_change", _d), ("edge_ratio", _d), ("local_contrast_change", _d),
+                ("gradient_strength_change", _d), ("gradient_entropy_change", _d)]
+
+
 STEP_NAMES = ("denoise", "clahe", "gamma", "unsharp", "post_denoise", "bilateral", "tv_denoise")
 FLAG_HALO, FLAG_NOISE_GUARD, FLAG_OVER_PROCESSED, FLAG_ERR_CLAHE_RANGE, FLAG_ERR_GAMMA_NEG = 1, 2, 4, 8, 16
 OP_ENHANCE = 15
@@ -92,6 +103,9 @@ PROTOTYPES.update({
     "mdimg_enhance_tables_default": (_i, [C.POINTER(EnhancePlan), _i, _i, C.POINTER(EnhanceTables)]),
     "mdimg_enhance": (_i, [_p, _p, _i, _i, _i, C.POINTER(EnhancePlan), C.POINTER(EnhanceTables), _p, _p,
                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), *_WS]),
+    "mdimg_detect_issues": (_i, [C.POINTER(_d)]),
+    "mdimg_validation_scalars_of": (_i, [C.POINTER(_d), C.POINTER(ValidationScalars)]),
+    "mdimg_objective_score": (_i, [C.POINTER(ValidationScalars), C.POINTER(_d), C.POINTER(_d)]),
     "mdimg_enhance_issues": (_i, [_p, _p, _i, _i, _i, _i, C.POINTER(EnhanceTables), _p, C.POINTER(C.c_int32), *_WS]),
 })
 

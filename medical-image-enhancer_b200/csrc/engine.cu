@@ -539,4 +539,70 @@ int mdimg_enhance_issues(const float* in, float* out, int n, int h, int w, int i
     return check_launch("enhance_issues");
 }
 
+// ---- host scalar logic (python-float arithmetic of pipeline/metrics.py, statement by statement) ----
+static inline double py_max(double a, double b) { return b > a ? b : a; }      // python max(a, b): a unless b > a
+static inline double py_min(double a, double b) { return b < a ? b : a; }      // python min(a, b)
+
+int mdimg_detect_issues(const double* m) {
+    if (!m) return 0;
+    int mask = 0;
+    if (m[MC_SIGMA] > 0.08) mask |= MDIMG_ISSUE_NOISE;
+    if (m[MC_LAP_VAR] < 0.001) mask |= MDIMG_ISSUE_BLUR;
+    if (m[MC_STD] < 0.12) mask |= MDIMG_ISSUE_LOW_CONTRAST;
+    if (m[MC_PCT_LOW] > 0.01) mask |= MDIMG_ISSUE_CLIPPING_LOW;
+    if (m[MC_PCT_HIGH] > 0.01) mask |= MDIMG_ISSUE_CLIPPING_HIGH;
+    return mask;
+}
+
+int mdimg_validation_scalars_of(const double* row, mdimg_validation_scalars* o) {
+    if (!row || !o) return set_error(MDIMG_ERR_INVALID, "validation scalars: bad arguments");
+    const double* mb = row;
+    const double* ma = row + MC_COLS;
+    const double eps = 1e-8;
+    o->ssim = row[2 * MC_COLS];
+    o->psnr = row[2 * MC_COLS + 1];
+    o->niqe_before = mb[MC_NIQE];
+    o->niqe_after = ma[MC_NIQE];
+    o->niqe_improved = o->niqe_after <= o->niqe_before;
+    o->contrast_gain = (ma[MC_STD] - mb[MC_STD]) / py_max(mb[MC_STD], eps);
+    o->sharpness_gain = (ma[MC_LAP_VAR] - mb[MC_LAP_VAR]) / py_max(mb[MC_LAP_VAR], eps);
+    const double noise_reduction = (mb[MC_SIGMA] - ma[MC_SIGMA]) / py_max(mb[MC_SIGMA], eps);
+    o->quality_improvement = 0.35 * o->contrast_gain + 0.35 * o->sharpness_gain + 0.30 * noise_reduction;
+    o->meets_ssim = o->ssim >= 0.70;
+    o->meets_psnr = o->psnr >= 22.0;
+    o->meets_improvement = o->quality_improvement >= 0.10;
+    o->passes = (o->meets_ssim && o->meets_psnr) || (o->meets_ssim && o->meets_improvement) ||
+                (o->meets_psnr && o->meets_improvement && o->niqe_improved);
+    o->noise_change = -noise_reduction;
+    o->entropy_change = ma[MC_ENTROPY] - mb[MC_ENTROPY];
+    o->snr_change = ma[MC_SNR] - mb[MC_SNR];
+    o->cnr_change = ma[MC_CNR] - mb[MC_CNR];
+    o->edge_density_change = ma[MC_EDGE_DENSITY] - mb[MC_EDGE_DENSITY];
+    o->histogram_spread_change = ma[MC_HIST_SPREAD] - mb[MC_HIST_SPREAD];
+    o->edge_ratio = ma[MC_EDGE_RATIO];
+    o->local_contrast_change = ma[MC_LOCAL_CONTRAST] - mb[MC_LOCAL_CONTRAST];
+    o->gradient_strength_change = ma[MC_GRAD_STRENGTH] - mb[MC_GRAD_STRENGTH];
+    o->gradient_entropy_change = ma[MC_GRAD_ENTROPY] - mb[MC_GRAD_ENTROPY];
+    return MDIMG_OK;
+}
+
+int mdimg_objective_score(const mdimg_validation_scalars* v, double* score, double parts[11]) {
+    if (!v || !score || !parts) return set_error(MDIMG_ERR_INVALID, "objective score: bad arguments");
+    auto capped = [](double x, double cap) { return py_max(0.0, py_min(x, cap)); };
+    parts[0] = v->contrast_gain;
+    parts[1] = v->sharpness_gain;
+    parts[2] = py_max(0.0, v->noise_change);
+    parts[3] = py_max(0.0, v->niqe_after - v->niqe_before);
+    parts[4] = py_max(0.0, v->edge_ratio - 1.0) * 5.0;
+    parts[5] = py_max(0.0, std::fabs(v->entropy_change) - 0.5) * 2.0;
+    parts[6] = capped(v->snr_change * 0.1, 0.5);
+    parts[7] = capped(v->histogram_spread_change * 0.5, 0.3);
+    parts[8] = capped(v->local_contrast_change * 0.3, 0.3);
+    parts[9] = capped(v->gradient_strength_change * 0.2, 0.2);
+    parts[10] = py_max(0.0, std::fabs(v->gradient_entropy_change) - 0.3) * 1.5;
+    *score = 0.35 * parts[0] + 0.35 * parts[1] - 0.30 * parts[2] - 5.0 * parts[3] - 10.0 * (v->passes ? 0 : 1)
+             - parts[4] - parts[5] + parts[6] + parts[7] + parts[8] + parts[9] - parts[10];
+    return MDIMG_OK;
+}
+
 }  // extern "C"

@@ -252,3 +252,59 @@ def test_default_tables_follow_numpy_and_scipy():
                 np.testing.assert_allclose(np.array(t.bilateral_spatial[:deff * deff]), spatial.ravel(), rtol=2.3e-16, atol=0)
             else:
                 assert t.bilateral_d_eff == 0
+
+
+def test_c_scalar_logic_equals_the_python_arithmetic():
+    """mdimg_detect_issues / mdimg_validation_scalars_of / mdimg_objective_score (host functions of the
+    library) against the statement-by-statement python restatement of pipeline/metrics.py:166-179,237-408
+    (itself pinned against the reference's own bytes in tests/test_oracle.py): equal to the last bit."""
+    import ctypes as C
+
+    from mdimg_b200 import _lib
+    from mdimg_b200.batch import ROW_COLS
+    lib = _lib.load_library()
+    rng = np.random.default_rng(21)
+    dp = C.POINTER(C.c_double)
+    n_pass = 0
+    for trial in range(400):
+        row = np.zeros(2 * ROW_COLS + 2)
+        row[:2 * ROW_COLS] = rng.random(2 * ROW_COLS) * rng.choice([1e-3, 0.1, 1.0, 30.0], 2 * ROW_COLS)
+        row[2 * ROW_COLS] = rng.uniform(0.4, 1.0)
+        row[2 * ROW_COLS + 1] = rng.uniform(10.0, 50.0)
+        if trial % 7 == 0:
+            row[rng.integers(0, 2 * ROW_COLS)] = np.nan            # NaN metrics (all-zero image) must propagate alike
+        if trial % 11 == 0:
+            row[0] = 0.0                                           # sigma_before = 0: the eps floor
+        if trial % 13 == 0:
+            row[2 * ROW_COLS + 1] = np.inf                         # identical images
+        mb = engine.metrics_dict(row[:ROW_COLS])
+        ma = engine.metrics_dict(row[ROW_COLS:2 * ROW_COLS])
+        want = engine.validation_dict(mb, ma, float(row[2 * ROW_COLS]), float(row[2 * ROW_COLS + 1]),
+                                      float(row[engine.MC_NIQE]), float(row[ROW_COLS + engine.MC_NIQE]),
+                                      float(row[ROW_COLS + engine.MC_EDGE_RATIO]))
+        v = _lib.ValidationScalars()
+        assert lib.mdimg_validation_scalars_of(row.ctypes.data_as(dp), C.byref(v)) == 0
+        for key in ("ssim", "psnr", "quality_improvement", "niqe_before", "niqe_after", "contrast_gain", "sharpness_gain",
+                    "noise_change", "entropy_change", "snr_change", "cnr_change", "edge_density_change",
+                    "histogram_spread_change", "edge_ratio", "local_contrast_change", "gradient_strength_change",
+                    "gradient_entropy_change"):
+            a, b = getattr(v, key), want[key]
+            assert a == b or (np.isnan(a) and np.isnan(b)), (key, a, b)
+        for key in ("meets_ssim", "meets_psnr", "meets_improvement", "passes", "niqe_improved"):
+            assert bool(getattr(v, key)) == bool(want[key]), key
+        n_pass += bool(want["passes"])
+        score = C.c_double()
+        parts = (C.c_double * 11)()
+        assert lib.mdimg_objective_score(C.byref(v), C.byref(score), parts) == 0
+        ref_score, ref_parts = engine.objective_score(want)
+        if not np.isnan(score.value):
+            assert round(float(score.value), 4) == ref_score
+        names = [k for k in ref_parts if k != "passes"]
+        assert len(names) == 11
+        for k, p in zip(names, parts):
+            assert round(float(p), 4) == ref_parts[k] or (np.isnan(p) and np.isnan(ref_parts[k])), k
+        mask = lib.mdimg_detect_issues(row.ctypes.data_as(dp))
+        from mdimg_b200.pipeline.metrics import detect_issues
+        got = [nm for nm, bit in _lib.ISSUE_BITS.items() if mask & bit]
+        assert got == detect_issues(mb)
+    assert 0 < n_pass < 400

@@ -6,6 +6,7 @@ Prints one JSON object; CUDA-event timing after a warm-up pass, inputs resident 
     python tools/bench_configs.py [c3_images] [c5_mpx]
 """
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -103,8 +104,10 @@ def main():
         events.append((fn.__name__, a, b))
 
     StackOps._call = timed_call
+    os.environ["MDIMG_NATIVE_ENGINE"] = "0"        # step calls issued from Python, so that each one is timed
     res3 = process_stack(dev, plan, chunk=16, ops=ops, workers=1)
     torch.cuda.synchronize()
+    os.environ.pop("MDIMG_NATIVE_ENGINE", None)
     StackOps._call = orig_call
     agg, cnt = defaultdict(float), defaultdict(int)
     for name, a, b in events:

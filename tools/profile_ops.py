@@ -4,6 +4,7 @@
 from __future__ import annotations
 
 import json
+import os
 import sys
 import time
 from collections import defaultdict
@@ -13,6 +14,8 @@ import numpy as np
 import torch
 
 ROOT = Path(__file__).resolve().parent.parent
+# per-operator timing needs the step calls issued from Python: mdimg_enhance would be one opaque call
+os.environ["MDIMG_NATIVE_ENGINE"] = "0"
 sys.path.insert(0, str(ROOT))
 
 from mdimg_b200 import synth  # noqa: E402

@@ -40,6 +40,14 @@ from oracle import restoration as ores  # noqa: E402
 
 
 def install_skimage_stand_in() -> None:
+    """No-op when the real scikit-image is importable: the vectors then pin the leaves as well."""
+    try:
+        import skimage  # noqa: F401
+        import skimage.restoration  # noqa: F401  (needs PyWavelets)
+        print("using the installed scikit-image", skimage.__version__, "- the vectors pin the leaves too")
+        return
+    except Exception:  # noqa: BLE001
+        pass
     sk = types.ModuleType("skimage")
     filters = types.ModuleType("skimage.filters")
     filters.laplace = lambda image: oflt.laplace(image)

@@ -217,3 +217,47 @@ def test_save_stack_round_trip():
 def test_gather_labels_without_a_process_group_is_the_identity():
     labels = [["a"], [], ["b", "c"]]
     assert gather_labels(labels) == labels
+
+
+# ---- two ranks: gather rows + labels, rank 0 persists the whole stack in one transaction --------
+def _persist_worker(rank, world, n_total, port, db_path):
+    import torch
+    import torch.distributed as dist
+
+    from mdimg_b200.shard import gather_labels, gather_rows, slice_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["MDIMG_DB_PATH"] = db_path
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    packed, labels = _packed_rows(n_total, seed=17)             # every rank builds the same table, keeps its span
+    a, b = slice_range(n_total, rank, world)
+    rows = gather_rows(torch.from_numpy(packed[a:b].copy()), n_total)
+    labs = gather_labels(labels[a:b])
+    if rank == 0:
+        storage.save_stack(rows.numpy(), labs, "cohort.dcm", run_ids=[f"g{i:03d}" for i in range(n_total)],
+                           plan_json='{"ops": []}')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_gather_and_rank0_persists(tmp_path):
+    import torch.multiprocessing as mp
+    n_total = 9                                                    # unequal spans: 5 + 4
+    db = str(tmp_path / "gathered" / "mdimg.db")
+    ctx = mp.get_context("spawn")
+    port = 29700 + (os.getpid() % 1500)
+    procs = [ctx.Process(target=_persist_worker, args=(r, 2, n_total, port, db)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    os.environ["MDIMG_DB_PATH"] = db
+    packed, labels = _packed_rows(n_total, seed=17)
+    rows = {r["run_id"]: r for r in storage.list_runs(limit=100)}
+    assert sorted(rows) == [f"g{i:03d}" for i in range(n_total)]
+    for i in range(n_total):
+        r = rows[f"g{i:03d}"]
+        assert r["metadata_summary"]["slice_index"] == i and r["applied_ops"] == labels[i]
+        assert r["metrics_before"] == engine.metrics_dict(packed[i, :ROW_COLS])
+        assert r["plan_json"] == '{"ops": []}' and r["status"] in ("PASS", "WARN", "FAIL")

@@ -181,12 +181,8 @@ int validation_pack_run(const Dims& d, const double* rows_a, const double* rows_
 }
 
 void launch_box16_stats(const float* img, const Dims& d, double* acc2, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_box16_stats, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(Box16Smem));
-        attr_set = true;
-    }
+    static unsigned long long devices_done = 0;
+    opt_in_shared_memory(k_box16_stats, sizeof(Box16Smem), devices_done);
     dim3 grid(((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH), d.n_sel);
     MDIMG_LAUNCH k_box16_stats<<<grid, NT, sizeof(Box16Smem), stream>>>(img, d, acc2);
 }
@@ -205,12 +201,8 @@ int fullref_run(const float* ia, const float* ib, const Dims& d, double* out, vo
     Arena a(ws, ws_bytes);
     double* acc2 = a.take<double>((size_t)d.n_sel * 2);
     if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "fullref: workspace too small");
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_ssim_psnr, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(SsimSmem));
-        attr_set = true;
-    }
+    static unsigned long long devices_done = 0;
+    opt_in_shared_memory(k_ssim_psnr, sizeof(SsimSmem), devices_done);
     cudaMemsetAsync(acc2, 0, sizeof(double) * 2 * d.n_sel, stream);
     dim3 grid(((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH), d.n_sel);
     MDIMG_LAUNCH k_ssim_psnr<<<grid, NT, sizeof(SsimSmem), stream>>>(ia, ib, d, acc2);

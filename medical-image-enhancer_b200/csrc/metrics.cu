@@ -709,12 +709,8 @@ int metrics_run(const float* img, const Dims& d, const PctPlan& plan, int flags,
     cudaMemsetAsync(m.l1x, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
     cudaMemsetAsync(m.l1g, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_stencil_stats, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(StencilSmem));
-        attr_set = true;
-    }
+    static unsigned long long devices_done = 0;
+    opt_in_shared_memory(k_stencil_stats, sizeof(StencilSmem), devices_done);
     dim3 grid(((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH), d.n_sel);
     MDIMG_LAUNCH k_stencil_stats<<<grid, NT, sizeof(StencilSmem), stream>>>(img, d, m.acc, m.g, m.l1x, m.l1g);
     int rc = check_launch("stencil_stats");

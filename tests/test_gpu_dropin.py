@@ -406,6 +406,29 @@ def test_native_issue_chain_equals_the_python_engine(ops, synth):
             fn(bad, ["low_contrast"])
 
 
+def test_two_devices_in_one_process(synth):
+    """The library holds no per-device state besides what it sets up per device (shared-memory opt-ins):
+    the same process can drive two GPUs (the multi-GPU path proper is one process per GPU)."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from mdimg_b200.batch import process_stack
+    from mdimg_b200.stack import get_ops
+    raw = np.stack([synth.ct_slice(6000 + z, z / 2, size=128) for z in range(2)])
+    plan = synth.plan_full()
+    results = []
+    for idx in (1, 0, 1):
+        dev = torch.device(f"cuda:{idx}")
+        ops_i = get_ops(dev)
+        with torch.cuda.device(dev):
+            res = process_stack(torch.from_numpy(raw.view(np.int16)).to(dev), plan, chunk=2, ops=ops_i)
+        results.append(res)
+    for res in results[1:]:
+        np.testing.assert_array_equal(res.enhanced.cpu().numpy(), results[0].enhanced.cpu().numpy())
+        np.testing.assert_allclose(res.packed, results[0].packed, rtol=1e-9, atol=1e-12)
+        assert res.labels == results[0].labels
+
+
 def test_score_plans_matches_the_tool_loop(ops, images, synth):
     """K candidate plans x N images (pipeline/tools.py:95-183 semantics) vs the oracle run one by one."""
     import torch

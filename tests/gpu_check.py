@@ -1,5 +1,5 @@
 """Developer parity report: every operator of the CUDA path vs the CPU oracle, with the actual
-error numbers (pytest only says pass/fail).  Run on a GPU box:  python tools/gpu_check.py [out.json]
+error numbers (pytest only says pass/fail).  Run on a GPU box:  python tests/gpu_check.py [out.json]
 """
 
 from __future__ import annotations

@@ -308,3 +308,22 @@ def test_c_scalar_logic_equals_the_python_arithmetic():
         got = [nm for nm, bit in _lib.ISSUE_BITS.items() if mask & bit]
         assert got == detect_issues(mb)
     assert 0 < n_pass < 400
+
+
+def test_constants_are_the_references_own():
+    """PARAM_BOUNDS, THRESHOLDS, ENHANCEMENT_PARAMS, the EnhancementParams defaults and the order of the 16
+    metric keys against values read from the reference's modules (tests/golden/make_reference_constants.py)."""
+    import json
+    from pathlib import Path
+
+    from mdimg_b200.pipeline.schemas import EnhancementParams
+    ref = json.loads((Path(__file__).resolve().parent / "golden" / "reference_constants.json").read_text())
+    assert {k: list(v) for k, v in engine.PARAM_BOUNDS.items()} == ref["PARAM_BOUNDS"]
+    assert list(engine.PARAM_BOUNDS) == list(ref["PARAM_BOUNDS"])
+    assert engine.THRESHOLDS == ref["THRESHOLDS"]
+    assert engine.ENHANCEMENT_PARAMS == ref["ENHANCEMENT_PARAMS"]
+    assert list(engine.METRIC_KEYS) == ref["metric_keys"]
+    mine = EnhancementParams().model_dump()
+    for k, v in ref["EnhancementParams_defaults"].items():
+        assert mine[k] == v, k
+    assert set(mine) <= set(ref["EnhancementParams_defaults"])

@@ -112,3 +112,14 @@ def test_plans_validation_and_scores(api, glue, images, name):
         score, breakdown = api.metrics.compute_objective_score(val)
         assert abs(score - g["score"][key]["score"]) <= 2e-4, key    # scores are rounded to 4 decimals
         assert breakdown["passes"] == g["score"][key]["breakdown"]["passes"]
+
+
+def test_normalize_image_against_the_references_own_output(api):
+    """The drop-in normalize_image against the reference's own function body run on 8 inputs of different
+    dtypes (tests/golden/make_reference_normalize.py): bit for bit."""
+    z = np.load(GOLDEN / "reference_normalize.npz")
+    for name in [k[3:] for k in z.files if k.startswith("in|")]:
+        got = api.dicom_io.normalize_image(z[f"in|{name}"])
+        want = z[f"out|{name}"]
+        assert got.dtype == np.float32 and got.shape == want.shape
+        np.testing.assert_array_equal(got, want, err_msg=name)

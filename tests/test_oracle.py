@@ -307,3 +307,17 @@ def test_restated_plan_enhancement_validation_and_score_equal_reference_source(s
                 assert _same(val[k], v), (key, k, val[k], v)
         score, breakdown = omet.compute_objective_score(val)
         assert score == g["score"][key]["score"] and breakdown == g["score"][key]["breakdown"], key
+
+
+def test_normalize_image_is_the_references_own_output():
+    """oracle normalize_image against vectors produced by the reference's own function body
+    (tests/golden/make_reference_normalize.py): bit for bit, every dtype."""
+    from pathlib import Path
+    z = np.load(Path(__file__).resolve().parent / "golden" / "reference_normalize.npz")
+    names = [k[3:] for k in z.files if k.startswith("in|")]
+    assert len(names) == 8
+    for name in names:
+        got = omet.normalize_image(z[f"in|{name}"])
+        want = z[f"out|{name}"]
+        assert got.dtype == np.float32 and got.shape == want.shape
+        np.testing.assert_array_equal(got, want, err_msg=name)

@@ -146,7 +146,7 @@ def run_reference(args) -> None:
                                    "are not installed, so the reference itself cannot be imported)"},
         "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -484,12 +484,29 @@ def run_gpu(args) -> None:
             "roofline": roof,
             "cpu_baseline": cpu_base,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line, written to the process's real stdout (see main: while the benchmark runs, file
+    descriptor 1 points at stderr, so that nothing a library prints -- NCCL announces its version on
+    stdout when the first communicator is created -- can land next to it)."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def main() -> None:
+    global _REAL_STDOUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -502,6 +519,9 @@ def main() -> None:
     ap.add_argument("--workers", type=int, default=4, help="host threads / CUDA streams driving chunks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     try:
         if args.impl == "reference":
             run_reference(args)

@@ -327,3 +327,18 @@ def test_constants_are_the_references_own():
     for k, v in ref["EnhancementParams_defaults"].items():
         assert mine[k] == v, k
     assert set(mine) <= set(ref["EnhancementParams_defaults"])
+
+
+def test_chunk_spans_cover_every_slice_once():
+    from mdimg_b200.batch import _spans_of, default_chunk
+    for n in (0, 1, 5, 64, 1000, 1024):
+        for chunk, schedule in ((7, None), (512, None), (1, None), (3, [4, 2, 1]), (9, [160, 124, 33]), (2, [1000000])):
+            spans = _spans_of(n, chunk, schedule)
+            assert [a for a, _ in spans] == [0] * (n > 0) + [b for _, b in spans[:-1]]
+            assert (spans[-1][1] if spans else 0) == n and all(b > a for a, b in spans)
+            if schedule:
+                want = [schedule[k % len(schedule)] for k in range(len(spans))]
+                assert [b - a for a, b in spans[:-1]] == want[:len(spans) - 1]
+    # ~128 Mpx per chunk, at least one image, at most 4096 slices
+    assert default_chunk(512, 512) == 512 and default_chunk(3000, 3000) == 14
+    assert default_chunk(100000, 100000) == 1 and default_chunk(8, 8) == 4096

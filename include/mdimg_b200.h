@@ -210,9 +210,11 @@ enum mdimg_step {            /* index into the reference's fixed step order (enh
     MDIMG_STEP_DENOISE = 0, MDIMG_STEP_CLAHE = 1, MDIMG_STEP_GAMMA = 2, MDIMG_STEP_UNSHARP = 3,
     MDIMG_STEP_POST_DENOISE = 4, MDIMG_STEP_BILATERAL = 5, MDIMG_STEP_TV_DENOISE = 6
 };
+#define MDIMG_MAX_PLAN_OPS 64    /* capacity of mdimg_enhance_plan.ops[]; a longer list is an error, never truncated */
 typedef struct mdimg_enhance_plan {
-    int32_t n_ops;               /* entries of ops[] */
-    int32_t ops[16];             /* plan.recommended_ops in the plan's order, as MDIMG_STEP_* (unknown names dropped) */
+    int32_t n_ops;               /* entries of ops[] (<= MDIMG_MAX_PLAN_OPS) */
+    int32_t ops[MDIMG_MAX_PLAN_OPS]; /* plan.recommended_ops in the plan's order, repeats included (the halo
+                                  * safeguard replays the list as written), as MDIMG_STEP_*; unknown names dropped */
     double clahe_clip_limit;     /* EnhancementParams (pipeline/schemas.py:36-100); clamped by mdimg_plan_clamp */
     int32_t clahe_tile_size;
     double gamma;

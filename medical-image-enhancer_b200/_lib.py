@@ -66,9 +66,12 @@ PROTOTYPES = {
 
 
 
+MAX_PLAN_OPS = 64        # MDIMG_MAX_PLAN_OPS
+
+
 class EnhancePlan(C.Structure):
     """mdimg_enhance_plan (include/mdimg_b200.h)."""
-    _fields_ = [("n_ops", C.c_int32), ("ops", C.c_int32 * 16),
+    _fields_ = [("n_ops", C.c_int32), ("ops", C.c_int32 * MAX_PLAN_OPS),
                 ("clahe_clip_limit", _d), ("clahe_tile_size", C.c_int32), ("gamma", _d),
                 ("unsharp_radius", _d), ("unsharp_amount", _d), ("denoise_hard", C.c_int32),
                 ("post_denoise_strength", _d), ("bilateral_d", C.c_int32),

@@ -231,7 +231,8 @@ int mdimg_plan_clamp(mdimg_enhance_plan* p) {
     p->bilateral_sigma_space = clampd(p->bilateral_sigma_space, 0.005, 0.20);
     p->tv_denoise_weight = clampd(p->tv_denoise_weight, 0.0, 0.15);
     if (p->n_ops < 0) p->n_ops = 0;
-    if (p->n_ops > 16) p->n_ops = 16;
+    if (p->n_ops > MDIMG_MAX_PLAN_OPS)      // never truncate: membership and the halo re-run depend on every entry
+        return set_error(MDIMG_ERR_INVALID, "plan lists %d operations, capacity is %d", p->n_ops, MDIMG_MAX_PLAN_OPS);
     return MDIMG_OK;
 }
 
@@ -296,7 +297,7 @@ int mdimg_enhance(const float* in, float* out, int n, int h, int w, const mdimg_
     if (n == 0) return MDIMG_OK;
     Ctx c;
     c.n = n; c.h = h; c.w = w; c.in = in; c.q = *plan; c.t = tables; c.stream = stream;
-    mdimg_plan_clamp(&c.q);
+    if (int rc0 = mdimg_plan_clamp(&c.q)) return rc0;
     const mdimg_enhance_plan& q = c.q;
     Arena a(ws, ws_bytes);
     carve(a, n, h, w, q.clahe_tile_size, c.b);

@@ -22,6 +22,13 @@ from .stack import StackOps
 
 logger = logging.getLogger("mdimg_b200.enhancement")
 
+
+def set_logger_name(name: str) -> None:
+    """Route the safeguard warnings to another logger: ``install_as_pipeline`` selects the reference's
+    ``pipeline.enhancement`` (pipeline/enhancement.py:26) so a host filtering by that name keeps them."""
+    global logger
+    logger = logging.getLogger(name)
+
 # pipeline/schemas.py:16-28
 PARAM_BOUNDS: Dict[str, Tuple[float, float]] = {
     "clahe_clip_limit": (0.002, 0.08),
@@ -378,7 +385,11 @@ class Engine:
                      on_error: str = "raise") -> EnhanceResult:
         """`enhance_from_params_native` (one library call) unless MDIMG_NATIVE_ENGINE=0 selects the torch-side
         control flow; the two are interchangeable (same pixels, flags, labels)."""
-        if os.environ.get("MDIMG_NATIVE_ENGINE", "1") != "0":
+        from . import _lib
+        known = sum(op.lower().strip() in _lib.STEP_NAMES for op in plan.recommended_ops)
+        # a list longer than the native call's ops[] capacity (repeats count: the halo safeguard replays
+        # the list as written) runs through the torch-side flow, which has no such limit
+        if os.environ.get("MDIMG_NATIVE_ENGINE", "1") != "0" and known <= _lib.MAX_PLAN_OPS:
             return self.enhance_from_params_native(image, plan, rows_before=rows_before, on_error=on_error)
         return self.enhance_from_params(image, plan, rows_before=rows_before, on_error=on_error)
 

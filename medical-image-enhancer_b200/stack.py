@@ -31,17 +31,17 @@ def percentile_plan(n: int, qs: Sequence[float] = (5, 25, 75, 95, 90)) -> Tuple[
     hi = np.zeros(len(qs), np.int32)
     gamma = np.zeros(len(qs), np.float32)
     for k, q in enumerate(qs):
-        quant = np.true_divide(q, np.float32(100), out=...)
-        virt = np.asanyarray((n - 1) * quant)
+        # explicit float32 scalars: no dependence on NEP 50 promotion or on ufunc keyword forms
+        quant = np.float32(q) / np.float32(100)
+        virt = np.float32(n - 1) * quant
         prev = np.floor(virt)
-        nxt = prev + 1
         if virt >= n - 1:
             prev_i, next_i = n - 1, n - 1
         elif virt < 0:
             prev_i, next_i = 0, 0
         else:
-            prev_i, next_i = int(prev), int(nxt)
-        g = np.asanyarray(virt - prev.astype(np.intp), dtype=virt.dtype)
+            prev_i, next_i = int(prev), int(prev) + 1
+        g = virt - np.float32(int(prev))
         lo[k], hi[k], gamma[k] = prev_i, next_i, np.float32(g)
     return lo, hi, gamma
 
@@ -347,7 +347,9 @@ class StackOps:
         n, h, w = self._img(image).shape
         q = _lib.EnhancePlan()
         names = [op.lower().strip() for op in plan.recommended_ops]
-        steps = [_lib.STEP_NAMES.index(nm) for nm in names if nm in _lib.STEP_NAMES][:16]
+        steps = [_lib.STEP_NAMES.index(nm) for nm in names if nm in _lib.STEP_NAMES]
+        if len(steps) > _lib.MAX_PLAN_OPS:       # Engine.enhance_plan routes such plans to the torch-side flow
+            raise ValueError(f"plan lists {len(steps)} recognised operations; the native call holds {_lib.MAX_PLAN_OPS}")
         q.n_ops = len(steps)
         for i, st in enumerate(steps):
             q.ops[i] = st

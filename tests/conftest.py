@@ -18,6 +18,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 
+LSB16 = 1.0 / 65535
+
+
+def assert_within_lsb(got, ref, what="", lsb=LSB16):
+    """north_star bar for pixels: max-abs <= 1 LSB of a 16-bit export, every pixel.  On failure the
+    worst pixel and the number of offenders are reported."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    if got.size == 0:
+        return
+    err = np.abs(got - ref)
+    worst = np.unravel_index(int(np.argmax(err)), err.shape)
+    assert err[worst] <= lsb, (
+        f"{what}: max |diff| = {err[worst]:.3e} = {err[worst] / LSB16:.2f} LSB at {worst} "
+        f"(got {got[worst]!r}, ref {ref[worst]!r}); {int((err > lsb).sum())} of {err.size} pixels over the bar")
+
+
 @pytest.fixture(scope="session")
 def synth():
     from mdimg_b200 import synth as s

@@ -84,3 +84,21 @@ def test_product_path_never_imports_the_oracle():
             assert "import oracle" not in src and "from oracle" not in src, py
     for c_src in list((ROOT / "medical-image-enhancer_b200" / "csrc").glob("*.cu*")) + list((ROOT / "examples").glob("*.c")):
         assert "oracle/" not in c_src.read_text(), c_src          # no include of, or path into, oracle/
+
+
+def test_plan_clamp_never_truncates_the_operation_list(lib):
+    """mdimg_plan_clamp is host arithmetic (no GPU): PARAM_BOUNDS clamping, and a list longer than
+    ops[] is an error instead of a silently shortened plan (the halo safeguard replays every entry)."""
+    import ctypes as C
+    from mdimg_b200 import _lib
+    q = _lib.EnhancePlan()
+    q.n_ops = _lib.MAX_PLAN_OPS
+    q.gamma, q.clahe_clip_limit, q.unsharp_amount, q.tv_denoise_weight = 9.0, 0.0, -1.0, 1.0
+    assert lib.mdimg_plan_clamp(C.byref(q)) == 0
+    assert (q.n_ops, q.gamma, q.clahe_clip_limit, q.unsharp_amount, q.tv_denoise_weight) == (
+        _lib.MAX_PLAN_OPS, 1.5, 0.002, 0.03, 0.15)
+    q.n_ops = _lib.MAX_PLAN_OPS + 1
+    assert lib.mdimg_plan_clamp(C.byref(q)) == 1
+    assert b"capacity" in lib.mdimg_last_error()
+    header = HEADER.read_text()
+    assert f"#define MDIMG_MAX_PLAN_OPS {_lib.MAX_PLAN_OPS}" in header

@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from mdimg_b200.engine import METRIC_KEYS
+from conftest import assert_within_lsb
 from oracle import ref_enhancement as oenh
 from oracle import ref_metrics as omet
 
@@ -99,8 +100,7 @@ def test_c2_slices_are_independent_and_match_the_oracle(ops, synth, ct_stack):
         x = omet.normalize_image(raw[z])
         ref, ref_labels = oenh.apply_enhancements_from_params(x, plan)
         assert res.labels[z] == ref_labels
-        d = np.abs(res.enhanced[z].cpu().numpy().astype(np.float64) - ref)
-        assert float((d > LSB16).mean()) < 0.01
+        assert_within_lsb(res.enhanced[z].cpu().numpy(), ref, f"C2 slice {z}")
         got = res.metrics_before(z)
         want = omet.compute_metrics(x)
         for k in METRIC_KEYS:

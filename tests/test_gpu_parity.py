@@ -23,6 +23,7 @@ pytestmark = pytest.mark.gpu
 NAMES = ["clean64", "noisy64", "lowc64", "ct512", "unit256", "odd94x141", "cr600"]
 ULP = 2.0 ** -23          # float32 spacing just below 1.0 is 2**-24; values here are <= 1
 LSB16 = 1.0 / 65535
+TV_BORDERLINE: set = set()     # (image name, weight) pairs whose stop test is within rounding of its threshold: none
 
 
 def host(t):
@@ -290,13 +291,16 @@ def test_tv_chambolle(ops, dev, images, name, weight):
     out = torch.empty_like(x)
     iters = int(ops.tv_chambolle(x, out, weight)[0].item())
     ref, ref_iters = ores.denoise_tv_chambolle(im, weight, return_iters=True)
-    # the stop test compares float32 energies whose summation order differs (float64 here, float32
-    # pairwise in numpy): a borderline test may move the stop by one iteration
-    assert abs(iters - ref_iters) <= 1
-    if iters == ref_iters:
-        np.testing.assert_array_equal(host(out), ref)
-    else:
-        assert np.abs(host(out) - ref).max() <= 1e-3
+    # The stop test compares float32 energies whose summation order differs (float64 here, float32
+    # pairwise in numpy), so a borderline |E_prev - E| < eps * E_0 could move the stop by one body.
+    # None of the committed cases is borderline: counts must be EQUAL and the field bit-exact.  A case
+    # that ever turns out borderline is listed by name in TV_BORDERLINE (and then held to 1 LSB).
+    if (name, weight) in TV_BORDERLINE:
+        assert abs(iters - ref_iters) <= 1
+        assert np.abs(host(out) - ref).max() <= LSB16
+        return
+    assert iters == ref_iters, (name, weight, iters, ref_iters)
+    np.testing.assert_array_equal(host(out), ref)
 
 
 def test_tv_in_place_and_iteration_cap(ops, dev, images):
@@ -325,9 +329,8 @@ def test_tv_kernel_variants_and_replay(ops, dev, monkeypatch, knobs, cap):
     eps = 2.0e-4 if cap == 200 else 0.0
     iters = int(ops.tv_chambolle(x, out, 0.08, eps=eps, max_iter=cap)[0].item())
     ref, ref_iters = ores.denoise_tv_chambolle(im, 0.08, eps=eps, max_num_iter=cap, return_iters=True)
-    assert abs(iters - ref_iters) <= 1
-    if iters == ref_iters:
-        np.testing.assert_array_equal(host(out), ref)
+    assert iters == ref_iters, (knobs, cap, iters, ref_iters)
+    np.testing.assert_array_equal(host(out), ref)
 
 
 def test_tv_stack_slices_stop_independently(ops):

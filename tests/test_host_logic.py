@@ -28,7 +28,7 @@ def _lerp32(a, b, t):
     return r
 
 
-@pytest.mark.parametrize("n", [7, 64 * 64, 512 * 512, 3000 * 3000, 94 * 141])
+@pytest.mark.parametrize("n", [1, 2, 7, 64 * 64, 512 * 512, 3000 * 3000, 94 * 141, 4096 * 4096])
 def test_percentile_plan_reproduces_numpy_bit_for_bit(n):
     x = np.random.default_rng(n).random(n).astype(np.float32)
     xs = np.sort(x)

@@ -1,0 +1,91 @@
+"""The drop-in under the reference's OWN callers.
+
+CPU part (needs the reference checkout, skipped without it): after ``install_as_pipeline()`` the
+reference's unmodified ``pipeline/core_agents.py`` and ``pipeline/tools.py`` hold the drop-in
+functions — whether they are imported after the call or were imported before it — and
+``pipeline.dicom_io`` keeps the reference's DICOM / report code with ``normalize_image`` replaced.
+
+GPU part: the agent chain QualityDetection -> Recommendation -> Enhancement -> Validation runs over
+the CUDA drop-in and reproduces the transcript that the reference's own agent classes produced
+(tests/golden/make_reference_agents.py) — metrics to 1e-5, pixels to 1 LSB, issues / labels /
+status / notes exactly, and the safeguard warnings arrive on the logger ``pipeline.enhancement``."""
+
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import assert_within_lsb
+
+HERE = Path(__file__).resolve().parent
+RUNNER = HERE / "agents_chain_runner.py"
+REFERENCE = Path("/root/reference")
+REL = 1.0e-5
+
+
+def _run(*args, timeout=600):
+    res = subprocess.run([sys.executable, str(RUNNER), *args], capture_output=True, text=True, timeout=timeout,
+                         env=dict(os.environ, PYTHONWARNINGS="ignore"))
+    assert res.returncode == 0, res.stderr[-4000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("RESULT_JSON ")][-1]
+    return json.loads(line[len("RESULT_JSON "):])
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="needs the reference checkout")
+@pytest.mark.parametrize("order", ["install-then-import", "import-then-install"])
+def test_reference_agents_hold_the_drop_in_functions(order):
+    out = _run("identity", *(["late"] if order == "import-then-install" else []))
+    assert out["agents_file"] == str(REFERENCE / "pipeline" / "core_agents.py")
+    assert all(out["same"].values()), out["same"]
+    assert "tools_import_error" not in out, out.get("tools_import_error")
+    assert out["installed"]["pipeline.dicom_io"] == ["normalize_image"]
+    assert out["logger"] == "pipeline.enhancement"
+    if order == "import-then-install":
+        assert sorted(out["installed"]["pipeline.core_agents"]) == [
+            "apply_enhancements", "compute_metrics", "compute_validation", "detect_issues"]
+
+
+def _close(a, b, rel=REL, floor=1e-6):
+    return a == b or abs(a - b) <= rel * max(abs(b), floor)
+
+
+@pytest.mark.gpu
+def test_agent_chain_reproduces_the_reference_transcript(tmp_path):
+    want = json.loads((HERE / "golden" / "reference_agents.json").read_text())
+    want_img = np.load(HERE / "golden" / "reference_agents.npz")
+    npz = tmp_path / "chain.npz"
+    got = _run("chain", str(npz))
+    got_img = np.load(npz)
+    for name, w in want.items():
+        g = got[name]
+        assert g["detection"]["issues"] == w["detection"]["issues"], name
+        assert list(g["detection"]["metrics"]) == list(w["detection"]["metrics"])
+        for k, v in w["detection"]["metrics"].items():
+            assert _close(g["detection"]["metrics"][k], v), (name, k, g["detection"]["metrics"][k], v)
+        assert g["enhancement"]["applied_ops"] == w["enhancement"]["applied_ops"], name
+        assert_within_lsb(got_img[name], want_img[name], f"agent chain {name}")
+        for k, v in w["enhancement"]["metrics"].items():
+            # metrics of the enhanced image: the two images agree to 1 LSB, not to the bit, so the
+            # derivative-type metrics carry that difference -> compared at 1e-4 here, at 1e-5 on
+            # identical inputs in test_gpu_reference_vectors.py
+            assert _close(g["enhancement"]["metrics"][k], v, rel=1e-4), (name, k, g["enhancement"]["metrics"][k], v)
+        gv, wv = g["validation"], w["validation"]
+        for k in ("status", "notes", "passes", "meets_ssim", "meets_psnr", "meets_improvement", "niqe_improved"):
+            assert gv[k] == wv[k], (name, k, gv[k], wv[k])
+        for k in ("ssim", "psnr", "niqe_before", "niqe_after"):
+            assert _close(gv[k], wv[k], rel=1e-4), (name, k, gv[k], wv[k])
+        for k in ("quality_improvement", "contrast_gain", "sharpness_gain", "noise_change"):
+            assert abs(gv[k] - wv[k]) <= 2e-4 * max(1.0, abs(wv[k])), (name, k, gv[k], wv[k])
+        if got["used_reference_agents"]:
+            assert g["report"].splitlines()[0] == w["report"].splitlines()[0]
+    # three of the four inputs trip the noise guard (see the transcript's labels): its warning must
+    # arrive under the reference's logger name
+    names = {n for n, _ in got["log_records"]}
+    assert names == {"pipeline.enhancement"}, got["log_records"]
+    assert sum("Noise amplification" in m for _, m in got["log_records"]) == 3

@@ -109,7 +109,7 @@ def cpu_pool(cores: int):
 def cpu_throughput(stack: np.ndarray, n_slices: int, cores: int):
     """Mpx/s of the restated reference on `n_slices` slices using `cores` processes."""
     sample = [stack[i] for i in np.linspace(0, stack.shape[0] - 1, n_slices).astype(int)]
-    pool = cpu_pool(cores)
+    pool = cpu_pool(cores) if cores > 1 else None
     t0 = time.perf_counter()
     if pool is not None:
         px = sum(pool.map(_cpu_one, sample, chunksize=1))
@@ -134,6 +134,8 @@ def run_reference(args) -> None:
         vals.append(v)
         times.append(dt)
     value = float(np.mean(vals))
+    _cpu_one(stack[0])
+    v1, dt1 = cpu_throughput(stack, 6, 1)        # single-core rate (BASELINE.md 4.3 asks for both)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3),
@@ -141,6 +143,8 @@ def run_reference(args) -> None:
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_slices_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cores, "kind": "port",
+                         "one_core": {"value": v1, "unit": "Mpx/s", "cores": 1,
+                                      "sample": f"6 slices in one process, {dt1:.1f} s wall"},
                          "sample": f"{per_step} of 1024 slices per step, one warm process per core; "
                                    "restated reference (numpy+scipy oracle; scikit-image/PyWavelets "
                                    "are not installed, so the reference itself cannot be imported)"},
@@ -278,6 +282,74 @@ def measured_hbm_gbs():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+# algorithmic bytes per pixel and call of every C-ABI operator of the step
+ALG_BYTES_PER_PX = {
+    "mdimg_normalize_u16": 8, "mdimg_metrics": 4, "mdimg_fullref": 8, "mdimg_wavelet_denoise": 12,
+    "mdimg_light_denoise": 16, "mdimg_clahe": 16, "mdimg_clahe_gamma": 16, "mdimg_gamma": 8, "mdimg_unsharp": 8,
+    "mdimg_bilateral": 8, "mdimg_clip01": 8, "mdimg_estimate_sigma": 4, "mdimg_quality": 4, "mdimg_axpby": 12,
+    "mdimg_copy": 8, "mdimg_export_u16": 6,
+}
+
+
+def operator_roofline(ops, raw_chunk, plan, peak):
+    """One chunk through the step with CUDA events around every C-ABI call (the torch-side control flow issues
+    the same operator calls that `mdimg_enhance` issues internally): per operator the device time, SURVEY
+    8(d)'s algorithmic bytes, achieved GB/s and the fraction of the measured HBM peak.  TV-Chambolle is
+    counted per launch as built (20 B/px per two-body launch -> 10 B/px per body, + 4 B/px result write)."""
+    import torch
+    from collections import defaultdict
+    from mdimg_b200.batch import process_stack
+    from mdimg_b200.stack import StackOps
+
+    n = int(raw_chunk.shape[0])
+    px = float(n) * H * W
+    prev_env = os.environ.get("MDIMG_NATIVE_ENGINE")
+    os.environ["MDIMG_NATIVE_ENGINE"] = "0"
+    orig_call = StackOps._call
+    try:
+        process_stack(raw_chunk, plan, chunk=n, ops=ops)          # warm-up in this mode
+        torch.cuda.synchronize()
+        events = []
+
+        def timed_call(self, fn, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig_call(self, fn, *a)
+            e1.record()
+            events.append((getattr(fn, "__name__", str(fn)), e0, e1))
+
+        StackOps._call = timed_call
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        res = process_stack(raw_chunk, plan, chunk=n, ops=ops)
+        t1.record()
+        torch.cuda.synchronize()
+    finally:
+        StackOps._call = orig_call
+        if prev_env is None:
+            os.environ.pop("MDIMG_NATIVE_ENGINE", None)
+        else:
+            os.environ["MDIMG_NATIVE_ENGINE"] = prev_env
+    ms, calls = defaultdict(float), defaultdict(int)
+    for name, e0, e1 in events:
+        ms[name] += e0.elapsed_time(e1)
+        calls[name] += 1
+    it_mean = float(res.tv_iterations.mean())
+    total = t0.elapsed_time(t1)
+    out = []
+    for name, t in sorted(ms.items(), key=lambda kv: -kv[1]):
+        b = 10.0 * it_mean + 4.0 if name == "mdimg_tv_chambolle" else ALG_BYTES_PER_PX.get(name)
+        entry = {"op": name, "calls": calls[name], "ms": round(t, 4), "share": round(t / total, 4)}
+        if b is not None:
+            gbs = b * px * calls[name] / (t / 1e3) / 1e9
+            entry.update(alg_bytes_per_px_per_call=b, achieved_gbs=round(gbs, 1), frac=round(gbs / peak, 4))
+        out.append(entry)
+    return {"slices": n, "pixels": px, "total_ms": round(total, 3), "tv_iterations_mean": it_mean, "peak_gbs": peak,
+            "basis": "SURVEY.md 8(d) algorithmic bytes x pixels x calls / CUDA-event time; "
+                     "frac = achieved / peak; TV per launch as built (10 B/px per body + 4)",
+            "ops": out}
+
+
 def run_gpu(args) -> None:
     import torch
     import torch.distributed as dist
@@ -408,7 +480,7 @@ def run_gpu(args) -> None:
     value = px_per_step * args.steps / (ms_total / 1e3) / 1e6
     e2e_value = px_per_step * e2e_steps / (ms_e2e / 1e3) / 1e6
 
-    # ---- roofline of the dominant kernel (TV-Chambolle body: 20 B/px algorithmic) ----
+    # ---- roofline of the dominant kernel + per-operator list --------------------------------------
     roof = None
     cpu_base = None
     if rank == 0:
@@ -426,34 +498,51 @@ def run_gpu(args) -> None:
             torch.cuda.synchronize()
             return a.elapsed_time(b)
         t_long, t_short = tv_ms(41), tv_ms(1)
-        per_launch_ms = (t_long - t_short) / 40.0
-        bytes_per_launch = 20.0 * chunk * H * W          # per loop body
+        bodies_per_launch = 2                             # k_tvp<2>: two Chambolle bodies per launch
+        per_launch_ms = (t_long - t_short) / 40.0 * bodies_per_launch
+        # Algorithmic bytes of ONE LAUNCH of the kernel as built (a lower bound on its DRAM traffic, so the
+        # fraction cannot exceed 1): x read once (4), p read once (8) and written once (8) = 20 B/px per
+        # launch, whatever the number of bodies fused inside.  SURVEY 8(d)'s 20 B/px PER BODY describes the
+        # unfused iteration; on that basis the same launch moves 40 B/px "algorithmically" (kept below).
+        bytes_per_launch = 20.0 * chunk * H * W
         achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9
         tv_iters = last.tv_iterations
         traffic = None
         tj = ROOT / "profiles" / "r01_tvp_traffic.json"
         if tj.exists():
             try:
-                traffic = float(json.loads(tj.read_text())["dram_bytes_per_pixel_per_body"]) * chunk * H * W
+                traffic = (float(json.loads(tj.read_text())["dram_bytes_per_pixel_per_body"]) * bodies_per_launch
+                           * chunk * H * W)
             except Exception:  # noqa: BLE001
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "k_tvp<2> (TV-Chambolle, packed two-pixel kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "k_tvp<2> (TV-Chambolle, packed two-pixel kernel, 2 bodies per launch)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per pixel and body "
-                                  "(profiles/r01_tvp_traffic.json) x pixels of this launch",
+                                  "(profiles/r01_tvp_traffic.json) x 2 bodies x pixels of this launch",
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "launch_ms": per_launch_ms,
-                "note": f"per loop body: 20 B/px (x 4 + p 8 read, p 8 written) x {chunk} slices x 512x512; one "
-                        f"k_tvp launch runs two bodies and keeps the intermediate p in registers, so its "
-                        f"DRAM traffic is about half the algorithmic figure (achieved can exceed the HBM peak); "
-                        f"measured limiter: FP32 pipe + issue, DRAM at 55 %; timed as (41 - 1 bodies) / 40 with "
-                        f"CUDA events; mean TV iterations/slice in the workload = {float(tv_iters.mean()):.1f}"}
+                "unfused_basis": {"bytes_per_px_per_body": 20.0,
+                                  "achieved_gbs": 2.0 * achieved, "frac": 2.0 * achieved / peak,
+                                  "note": "SURVEY 8(d) counts 20 B/px for every loop body; two bodies share one "
+                                          "pass over x and p here, so this figure is not a lower bound on traffic "
+                                          "and may exceed 1 -- reported for comparison only"},
+                "note": f"one launch = 2 bodies over {chunk} slices x 512x512: x 4 B read + p 8 B read + p 8 B written "
+                        f"per pixel; timed as (41 - 1 bodies) / 20 launches with CUDA events on the launching stream; "
+                        f"measured limiter: FP32 pipe + issue, DRAM ~55 % busy; "
+                        f"mean TV iterations/slice in the workload = {float(tv_iters.mean()):.1f}"}
+        del x, y
+        roof["operators"] = operator_roofline(ops, raw_dev[:chunk], plan, peak)
         if not args.no_cpu and world == 1:     # the CPU leg is an N=1 measurement (rank 0 would share the host with 7 busy ranks)
             cores = len(os.sched_getaffinity(0))
             sample = max(4 * cores, 32)
             cpu_throughput(stack, cores, cores)          # warm the pool (not timed)
             v, dt = cpu_throughput(stack, sample, cores)
+            _cpu_one(stack[0])                           # warm this process
+            v1, dt1 = cpu_throughput(stack, 6, 1)        # the single-core rate beside it
             cpu_base = {"value": v, "unit": "Mpx/s", "cores": cores, "kind": "port",
+                        "one_core": {"value": v1, "unit": "Mpx/s", "cores": 1,
+                                     "sample": f"6 of {n} slices in this process, {dt1:.1f} s wall"},
                         "sample": f"{sample} of {n} slices, one warm process per core, {dt:.1f} s wall; restated "
                                   "reference (numpy+scipy oracle; scikit-image/PyWavelets not installed)"}
 

@@ -24,6 +24,7 @@ import pytest
 from conftest import assert_within_lsb
 
 HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE / "golden"))
 RUNNER = HERE / "agents_chain_runner.py"
 REFERENCE = Path("/root/reference")
 REL = 1.0e-5
@@ -70,18 +71,27 @@ def test_agent_chain_reproduces_the_reference_transcript(tmp_path):
             assert _close(g["detection"]["metrics"][k], v), (name, k, g["detection"]["metrics"][k], v)
         assert g["enhancement"]["applied_ops"] == w["enhancement"]["applied_ops"], name
         assert_within_lsb(got_img[name], want_img[name], f"agent chain {name}")
+        # Float outputs downstream of the enhanced image: the drop-in's image agrees with the transcript's
+        # to 1 LSB, not to the bit, so (a) against the transcript they are held to the accuracy that
+        # difference allows, and (b) against the oracle evaluated on the drop-in's OWN image -- identical
+        # input on both sides -- to north_star's 1e-5.
+        from make_reference_agents import chain_inputs
+        from oracle import ref_metrics as omet
+        original = chain_inputs()[name]
+        same_input = omet.compute_metrics(got_img[name])
         for k, v in w["enhancement"]["metrics"].items():
-            # metrics of the enhanced image: the two images agree to 1 LSB, not to the bit, so the
-            # derivative-type metrics carry that difference -> compared at 1e-4 here, at 1e-5 on
-            # identical inputs in test_gpu_reference_vectors.py
-            assert _close(g["enhancement"]["metrics"][k], v, rel=1e-4), (name, k, g["enhancement"]["metrics"][k], v)
+            assert _close(g["enhancement"]["metrics"][k], same_input[k]), (name, k, g["enhancement"]["metrics"][k], same_input[k])
+            assert _close(g["enhancement"]["metrics"][k], v, rel=2e-3, floor=1e-4), (name, k, g["enhancement"]["metrics"][k], v)
         gv, wv = g["validation"], w["validation"]
         for k in ("status", "notes", "passes", "meets_ssim", "meets_psnr", "meets_improvement", "niqe_improved"):
             assert gv[k] == wv[k], (name, k, gv[k], wv[k])
+        ov = omet.compute_validation(original, got_img[name])
         for k in ("ssim", "psnr", "niqe_before", "niqe_after"):
-            assert _close(gv[k], wv[k], rel=1e-4), (name, k, gv[k], wv[k])
+            assert _close(gv[k], ov[k]), (name, k, gv[k], ov[k])
+            assert _close(gv[k], wv[k], rel=2e-3), (name, k, gv[k], wv[k])
         for k in ("quality_improvement", "contrast_gain", "sharpness_gain", "noise_change"):
-            assert abs(gv[k] - wv[k]) <= 2e-4 * max(1.0, abs(wv[k])), (name, k, gv[k], wv[k])
+            assert abs(gv[k] - ov[k]) <= 2e-5 * max(1.0, abs(ov[k])), (name, k, gv[k], ov[k])
+            assert abs(gv[k] - wv[k]) <= 2e-3 * max(1.0, abs(wv[k])), (name, k, gv[k], wv[k])
         if got["used_reference_agents"]:
             assert g["report"].splitlines()[0] == w["report"].splitlines()[0]
     # three of the four inputs trip the noise guard (see the transcript's labels): its warning must

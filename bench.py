@@ -350,13 +350,35 @@ def operator_roofline(ops, raw_chunk, plan, peak):
             "ops": out}
 
 
+def gpu_cpu_affinity(index: int):
+    """Bind this rank (its host threads and the pages of its pinned buffers, which are allocated afterwards)
+    to the CPUs NVML reports as local to its GPU.  On a single-NUMA virtual machine this is the whole
+    machine and changes nothing; on a two-socket host it keeps the copies off the inter-socket link.
+    Returns the CPU list that was set, or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis else index
+        handle = nv.nvmlDeviceGetHandleByIndex(phys)
+        words = nv.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def run_gpu(args) -> None:
     import torch
     import torch.distributed as dist
 
     from mdimg_b200 import synth
-    from mdimg_b200.batch import (PACK_COLS, default_chunk, process_stack, process_stacks_host,
-                                  tapered_schedule)
+    from mdimg_b200.batch import PACK_COLS, default_chunk, tapered_schedule
+    from mdimg_b200.shard import process_cohort
     from mdimg_b200.stack import get_ops
 
     rank = int(os.environ.get("RANK", "0"))
@@ -364,6 +386,7 @@ def run_gpu(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device(f"cuda:{local}")
+    affinity = gpu_cpu_affinity(local) if (world > 1 and not args.no_affinity) else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -376,7 +399,6 @@ def run_gpu(args) -> None:
     pinned_in = torch.from_numpy(stack.view(np.int16)).pin_memory()
     pinned_out = torch.empty((n, H, W), dtype=torch.float32, pin_memory=True)
     raw_dev = pinned_in.to(device)
-    gathered = torch.empty((world * n, PACK_COLS), dtype=torch.float64, device=device) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -384,11 +406,12 @@ def run_gpu(args) -> None:
         torch.cuda.synchronize()
 
     def step_resident():
-        res = process_stack(raw_dev, plan, chunk=chunk, keep_enhanced=True, ops=ops, workers=args.workers)
-        if world > 1:   # the only exchange: per-slice metric / validation rows
-            rows = torch.from_numpy(res.packed).to(device)
-            dist.all_gather_into_tensor(gathered, rows)
-        return res
+        # the product's multi-GPU entry point: this rank's own volume (C4 style, inputs per rank) through the
+        # stack pipeline, then ONE all-gather of the device-resident result rows (no host round trip)
+        coh = process_cohort([raw_dev], plan, already_sharded=True, chunk=chunk, keep_enhanced=True, ops=ops,
+                             workers=args.workers)
+        assert coh.rows.shape[0] == world * n
+        return coh.local[0][4]
 
     # several chunks per stack so copies overlap compute; the first copy-in and the last copy-out
     # cannot overlap anything, so the chunks of the end-to-end path are smaller than the resident ones
@@ -407,15 +430,13 @@ def run_gpu(args) -> None:
     def cohort_e2e(k, u16=False):
         """k stacks through the public host-buffer API in one call: the chunks of all k stacks form one
         queue, so a stack's last copy-out overlaps the next stack's compute (outputs double-buffered)."""
-        results = process_stacks_host([stack] * k, plan, chunk=e2e_chunk, ops=ops, pinned_ins=[pinned_in] * k,
-                                      pinned_outs=[(pinned_outs16 if u16 else pinned_outs)[i % 2] for i in range(k)],
-                                      workers=args.workers, schedule=e2e_schedule,
-                                      out_dtype=np.uint16 if u16 else np.float32)
-        if world > 1:
-            for _, res in results:
-                rows = torch.from_numpy(res.packed).to(device)
-                dist.all_gather_into_tensor(gathered, rows)
-        return results[-1][1]
+        coh = process_cohort([stack] * k, plan, already_sharded=True, chunk=e2e_chunk, ops=ops,
+                             pinned_ins=[pinned_in] * k,
+                             pinned_outs=[(pinned_outs16 if u16 else pinned_outs)[i % 2] for i in range(k)],
+                             workers=args.workers, schedule=e2e_schedule,
+                             out_dtype=np.uint16 if u16 else np.float32)
+        assert coh.rows.shape[0] == world * n * k
+        return coh.local[-1][4]
 
     def timed_e2e(steps, warmup, u16=False):
         for _ in range(warmup):
@@ -553,6 +574,8 @@ def run_gpu(args) -> None:
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "slices_per_gpu": n, "chunk_slices": chunk, "workers": args.workers,
                        "l2": "input stack (512 MiB u16 per GPU) is larger than L2; no flush needed",
+                       "api": "shard.process_cohort (per-rank volume -> stack pipeline -> all-gather of device-resident rows)",
+                       "cpu_affinity_rank0": (f"{len(affinity)} CPUs local to the GPU" if affinity else None),
                        "images_per_s": value * 1e6 / (H * W), "ms_each_step_rank0": steps_ms},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpx/s",
@@ -607,6 +630,7 @@ def main() -> None:
     ap.add_argument("--e2e-schedule", default="", help="comma-separated chunk sizes of the end-to-end leg")
     ap.add_argument("--workers", type=int, default=4, help="host threads / CUDA streams driving chunks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind ranks to their GPU's local CPUs (N > 1)")
     args = ap.parse_args()
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)

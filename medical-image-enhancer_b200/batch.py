@@ -34,6 +34,8 @@ class StackResult:
     enhanced: Optional[torch.Tensor]        # [N, H, W] float32 on the device (None if not kept)
     packed: np.ndarray                      # [N, PACK_COLS] float64 on the host
     labels: List[List[str]]
+    packed_dev: Optional[torch.Tensor] = None   # the same rows, still on the device: the send buffer of the
+                                                # multi-GPU row gather (shard.process_cohort), no host round trip
 
     @property
     def rows_before(self) -> np.ndarray:
@@ -181,7 +183,7 @@ def process_stack(raw: torch.Tensor, plan, chunk: Optional[int] = None, keep_enh
         if errors:
             raise errors[0]
     flat = [lab for part in labels for lab in (part or [])]
-    return StackResult(enhanced=enhanced, packed=packed_dev.cpu().numpy(), labels=flat)
+    return StackResult(enhanced=enhanced, packed=packed_dev.cpu().numpy(), labels=flat, packed_dev=packed_dev)
 
 
 _stream_cache: dict = {}
@@ -236,7 +238,7 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
     ops = ops or get_ops()
     dev = ops.device
     nstk = len(raw_hosts)
-    srcs, outs, packs, jobs, labels = [], [], [], [], []
+    srcs, outs, packs, packs_dev, jobs, labels = [], [], [], [], [], []
     for k, raw_host in enumerate(raw_hosts):
         n, h, w = raw_host.shape
         pin = pinned_ins[k] if pinned_ins is not None else None
@@ -259,6 +261,7 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
         srcs.append(src_t)
         outs.append(out_t)
         packs.append(torch.empty((n, PACK_COLS), dtype=torch.float64, pin_memory=True))
+        packs_dev.append(torch.empty((n, PACK_COLS), dtype=torch.float64, device=dev))
         spans = _spans_of(n, chunk or default_chunk(h, w), schedule)
         labels.append([None] * len(spans))
         jobs.extend((k, j, a, b) for j, (a, b) in enumerate(spans))
@@ -299,6 +302,7 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
                         enh, packed, lab = process_chunk(ops, raw_d, plan, True)
                         if as_u16:
                             enh = ops.export_u16(enh)
+                        packs_dev[k][a:b].copy_(packed)          # device-resident copy of the rows (gather send buffer)
                         done = torch.cuda.Event()
                         done.record(main)
                         with torch.cuda.stream(copy_out):
@@ -329,7 +333,8 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
         flat = [lab for part in labels[k] for lab in (part or [])]
         out_np = outs[k].numpy()
         results.append((out_np.view(np.uint16) if as_u16 else out_np,
-                        StackResult(enhanced=None, packed=packs[k].numpy().copy(), labels=flat)))
+                        StackResult(enhanced=None, packed=packs[k].numpy().copy(), labels=flat,
+                                    packed_dev=packs_dev[k])))
     return results
 
 

@@ -11,6 +11,7 @@
 //   k_finalize      : the 16 numbers (+ mean, edge ratio, NIQE) per slice
 #include "metrics.cuh"
 #include "boxfilter.cuh"
+#include <cstdlib>
 
 namespace mdimg {
 
@@ -238,6 +239,374 @@ k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Strip kernel: ONE read of the image for the Laplacian / Sobel statistics, |grad| (written), the
+// 7x7 box local std (metrics.py:120-129), the 16x16 box local variance of the NIQE approximation
+// (metrics.py:195-200), clip counters, the 256-bin histogram and the level-1 select histograms.
+//
+// A block owns a strip of SW = 128 output columns (+ 8 / 7 halo columns: the 16-wide window
+// [i-8, i+7] bounds every other halo) and marches down a band of rows, SR = 8 rows per step:
+//   load   rows enter a 24-row ring in shared memory as DOUBLES (x and the float32-rounded x*x):
+//          one conversion per loaded pixel, none in any window below; the next step's rows are
+//          prefetched into registers while this step computes;
+//   V      axis-0 box sums: 143 threads slide the 16-row window, 134 threads the 7-row window down
+//          their column; the running sums live in registers for the whole band, so no window is ever
+//          warmed up twice.  scipy stores the axis-0 result as float32: the double is rounded to
+//          float32 precision ON THE FP64 PIPE ((v + C) - C with C = 1.5 * 2^(exponent + 29)), not
+//          through two conversions, and stays a double in shared memory;
+//   H      axis-1 box sums: (row, 8-column segment) threads slide along their segment; only the final
+//          means become float32 (scipy's output dtype), followed by the float32 variance arithmetic;
+//   S      3x3 stencils from the ring in double (scipy.ndimage.convolve accumulates in double and
+//          rounds once), histograms, counters, |grad| store.
+// Conversions issue on the 16-lane XU pipe, which bounded the previous tile kernels (XU 60-80 %
+// busy, ~50 conversions per pixel for the same work); here ~13 per pixel remain.
+// ---------------------------------------------------------------------------------------
+namespace strip {
+
+constexpr int NT = 320;               // 10 warps: axis-0 tasks on 5 + 5 warps (143 + 134 columns), axis-1 and stencils on 8
+constexpr int SW = 128;               // output columns per strip
+constexpr int HL = 8, HR = 7;         // halo of the 16-wide window [i-8, i+7]
+constexpr int SWP = SW + HL + HR;     // 143 input columns
+constexpr int P = 145;                // row pitch in doubles, = 1 (mod 16): conflict-free (row, segment) walks
+constexpr int SR = 8;                 // rows per step
+constexpr int RING = 3 * SR;          // ring rows: load blocks B, B+1, B+2 serve output block B
+constexpr int BLK = SR * P;           // doubles per ring block
+constexpr int NV16 = SWP;             // axis-0 tasks of the 16-window: every input column (threads 0..142)
+constexpr int NV7 = SW + 6;           // axis-0 tasks of the 7-window: input columns 5 .. SW+10 (threads 160..293)
+constexpr int SEG = 8;                // axis-1: outputs per (row, segment) task
+constexpr int NACC = 11;
+
+struct Smem {
+    double Xs[RING * P];              // x
+    double Xq[RING * P];              // float32(x * x)
+    double V[4][SR * P];              // axis-0 means: 16-window of x, of x*x; 7-window of x, of x*x
+    unsigned h256[256];
+    unsigned hx[SEL_L1_BINS];
+    unsigned hg[SEL_L1_BINS];
+    double red[NACC * 32];
+};
+
+// v rounded to float32 precision, as a double.  FAST: v is 0 or a normal float32-range magnitude
+// (guaranteed by the caller); the sum lands in the binade whose double spacing is the float32
+// spacing of v, where the FP64 adder's round-to-nearest-even is float32's.
+template <bool FAST>
+__device__ __forceinline__ double round_to_f32(double v) {
+    if (FAST) {
+        const int e = __double2hiint(v) & 0x7ff00000;
+        const double c = __hiloint2double(e + 0x01d80000, 0);     // 1.5 * 2^(exponent + 29)
+        return __dsub_rn(__dadd_rn(v, c), c);
+    }
+    return (double)(float)v;
+}
+
+// float32 bits of a double that holds a float32 value (0 or normal float32 range, any sign)
+__device__ __forceinline__ float f32_bits_of(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mag = hi & 0x7fffffffu;
+    const unsigned b = __funnelshift_l(lo, mag - 0x38000000u, 3) | (hi & 0x80000000u);
+    return __uint_as_float(mag ? b : (hi & 0x80000000u));
+}
+
+// level-1 select bin and 256-bin index without a float->int conversion (same values as sel_bin1 /
+// int(x * 256): the add with 2^23 in round-up / round-down mode leaves ceil / floor in the mantissa)
+__device__ __forceinline__ int bin1_fp(float v) {
+    const float t = fminf(fmaxf(__fmul_rn(v, 1021.0f), 0.0f), 2048.0f);
+    const int c = __float_as_int(__fadd_ru(t, 8388608.0f)) & 0x7fffff;
+    const int b = 1 + min(c, 1022);
+    return v < 0.0f ? 0 : b;
+}
+__device__ __forceinline__ int bin256_fp(float x) {
+    const float t = fminf(fmaxf(__fmul_rn(x, 256.0f), 0.0f), 1024.0f);
+    const int c = __float_as_int(__fadd_rd(t, 8388608.0f)) & 0x7fffff;
+    return min(c, 255);
+}
+
+// Offsets (in doubles) of ring rows relative to the first row of output block B: row r in [0, 24)
+// lives in load block B + r/8, whose ring block offset is o[r/8].
+struct RingOff { int o0, o1, o2; };
+__device__ __forceinline__ int ring_at(const RingOff& o, int r) {      // r is a compile-time constant after unrolling
+    return (r < SR ? o.o0 : (r < 2 * SR ? o.o1 : o.o2)) + (r & (SR - 1)) * P;
+}
+
+// ---- V: one step of the axis-0 window K of this thread's column vc ----
+template <int K, bool FAST>
+__device__ __forceinline__ void vertical(Smem& sm, const RingOff& o, bool first, int vc, double& vs, double& vq) {
+    constexpr int lead = K == 16 ? 15 : 11;      // row entering the window, relative to the output row
+    constexpr int tail = K == 16 ? 0 : 5;        // row leaving it after the output
+    const double inv = K == 16 ? 0.0625 : 1.0 / 7.0;
+    double* vS = sm.V[K == 16 ? 0 : 2] + vc;
+    double* vQ = sm.V[K == 16 ? 1 : 3] + vc;
+    const double* xs = sm.Xs + vc;
+    const double* xq = sm.Xq + vc;
+    if (first) {                                 // fresh window sums at the top of the band
+        vs = 0.0; vq = 0.0;
+#pragma unroll
+        for (int r = tail; r < lead; ++r) {
+            vs += xs[ring_at(o, r)];
+            vq += xq[ring_at(o, r)];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SR; ++j) {
+        const int ra = ring_at(o, j + lead);
+        vs += xs[ra];
+        vq += xq[ra];
+        vS[j * P] = round_to_f32<FAST>(vs * inv);
+        vQ[j * P] = round_to_f32<FAST>(vq * inv);
+        const int rt = ring_at(o, j + tail);
+        vs -= xs[rt];
+        vq -= xq[rt];
+    }
+}
+
+// ---- H: the SEG outputs (row j, columns SEG*g ..) of window K; f(i, mean of x, mean of x*x), float32 means ----
+template <int K, typename F>
+__device__ __forceinline__ void horizontal(const double* vS, const double* vQ, int j, int g, F&& f) {
+    constexpr int lead = K == 16 ? 15 : 11;
+    constexpr int tail = K == 16 ? 0 : 5;
+    const double inv = K == 16 ? 0.0625 : 1.0 / 7.0;
+    const double* rs = vS + j * P + SEG * g;
+    const double* rq = vQ + j * P + SEG * g;
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int k = tail; k < lead; ++k) { s += rs[k]; q += rq[k]; }
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) {
+        s += rs[i + lead];
+        q += rq[i + lead];
+        f(i, (float)(s * inv), (float)(q * inv));
+        s -= rs[i + tail];
+        q -= rq[i + tail];
+    }
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(NT, 2)
+k_strip_stats(const float* __restrict__ img, Dims d, int band_h, int want16, MetAcc* __restrict__ acc,
+              float* __restrict__ gout, unsigned* __restrict__ l1x, unsigned* __restrict__ l1g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    __shared__ int slow_s;
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    const int strips = (d.w + SW - 1) / SW;
+    const int strip_i = blockIdx.x % strips, band_i = blockIdx.x / strips;
+    const int x0 = strip_i * SW, yb0 = band_i * band_h;
+    const int bh = min(band_h, d.h - yb0);
+    const int nsteps = (bh + SR - 1) / SR;
+    const float* src = img + (size_t)s * d.h * d.w;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (FULL) {
+        for (int i = tid; i < 256; i += NT) sm.h256[i] = 0;
+        for (int i = tid; i < SEL_L1_BINS; i += NT) { sm.hx[i] = 0; sm.hg[i] = 0; }
+    }
+    if (tid == 0) slow_s = 0;
+    __syncthreads();
+
+    // ---- loader: warp w < 8 owns row w of a load block, a lane its columns lane + 32 k ----
+    constexpr int NC = (SWP + 31) / 32;           // 5
+    int gx[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) gx[k] = refl_sym_fast(x0 - HL + lane + 32 * k, d.w);
+    float pf[NC];
+    bool bad = false;
+    auto fetch = [&](int lb) {                    // load block lb -> registers
+        if (wid < SR) {
+            const float* row = src + (size_t)refl_sym_fast(yb0 - HL + lb * SR + wid, d.h) * d.w;
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (lane + 32 * k < SWP) pf[k] = row[gx[k]];
+        }
+    };
+    auto stash = [&](int off) {                   // registers -> the ring block at offset `off`, as doubles
+        if (wid < SR) {
+            const int r = off + wid * P + lane;
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (lane + 32 * k < SWP) {
+                    const float v = pf[k];
+                    // the FP64-pipe rounding needs 0 or a normal magnitude whose square is normal too
+                    const unsigned u = __float_as_uint(v);
+                    bad |= (u != 0u) && (u - 0x21800000u >= 0x3c000000u);      // outside [2^-60, 2^60) or negative
+                    sm.Xs[r + 32 * k] = (double)v;
+                    sm.Xq[r + 32 * k] = (double)__fmul_rn(v, v);
+                }
+        }
+    };
+
+    double vs = 0.0, vq = 0.0;                    // axis-0 window sums of this thread's column (whole band)
+    double a_x = 0.0, a_x2 = 0.0, a_lap = 0.0, a_lap2 = 0.0, a_abs = 0.0, a_g = 0.0, a_g2 = 0.0;
+    double a_b1 = 0.0, a_b2 = 0.0;                // axis-1 role's pair: (sum ls, sum ls^2) or (sum lv, sum lv^2)
+    unsigned c_low = 0, c_high = 0;
+    float gmax = 0.0f;
+    float* gdst = FULL ? gout + (size_t)s * d.h * d.w : nullptr;
+
+    RingOff o = {0, BLK, 2 * BLK};
+    fetch(0); stash(o.o0);
+    fetch(1); stash(o.o1);
+    fetch(2);
+    bool slow = false;
+    for (int B = 0; B < nsteps; ++B) {
+        stash(o.o2);
+        if (B + 1 < nsteps) fetch(B + 3);
+        if (bad && !slow) slow_s = 1;             // sticky for the rest of the band
+        __syncthreads();
+        slow = slow_s != 0;
+
+        // ---- V: warps 0-4 the 16-window (143 columns), warps 5-9 the 7-window (134 columns) ----
+        if (wid < 5) {
+            if (want16 && tid < NV16) {
+                if (!slow) vertical<16, true>(sm, o, B == 0, tid, vs, vq);
+                else vertical<16, false>(sm, o, B == 0, tid, vs, vq);
+            }
+        } else if (FULL && tid - 160 < NV7) {
+            if (!slow) vertical<7, true>(sm, o, B == 0, 5 + tid - 160, vs, vq);
+            else vertical<7, false>(sm, o, B == 0, 5 + tid - 160, vs, vq);
+        }
+        __syncthreads();
+
+        if (wid < 8) {
+            // ---- H: (row, 8-column segment) tasks; warps 0-3 the 16-window, warps 4-7 the 7-window ----
+            {
+                const int u = tid & 127;
+                const int j = u & 7, g = u >> 3;
+                const bool rowok = B * SR + j < bh;
+                const int xlim = d.w - x0 - SEG * g;           // outputs i < xlim are inside the image
+                if (wid < 4) {
+                    if (want16)
+                        horizontal<16>(sm.V[0], sm.V[1], j, g, [&](int i, float m, float q) {
+                            const float lv = fmaxf(__fsub_rn(q, __fmul_rn(m, m)), 0.0f);
+                            const double dl = (rowok && i < xlim) ? (double)lv : 0.0;
+                            a_b1 += dl;
+                            a_b2 = fma(dl, dl, a_b2);
+                        });
+                } else if (FULL) {
+                    horizontal<7>(sm.V[2], sm.V[3], j, g, [&](int i, float m, float q) {
+                        const float lv = fmaxf(__fsub_rn(q, __fmul_rn(m, m)), 0.0f);
+                        const double dl = (rowok && i < xlim) ? (double)sqrt_rn_fast(lv) : 0.0;
+                        a_b1 += dl;
+                        a_b2 = fma(dl, dl, a_b2);
+                    });
+                }
+            }
+            // ---- S: 3x3 stencils, a thread owns 4 rows of one column ----
+            const int col = tid & 127, rg = tid >> 7;
+            const int cc = col + HL;
+            const int gxo = x0 + col;
+            const bool colok = gxo < d.w;
+            const double* xs = sm.Xs + cc;
+            // ring rows 7 + 4 rg .. : the row above this thread's first output row, ...
+            double u0, u1, u2, m0, m1, m2;
+            if (rg == 0) {
+                u0 = xs[ring_at(o, 7) - 1]; u1 = xs[ring_at(o, 7)]; u2 = xs[ring_at(o, 7) + 1];
+                m0 = xs[ring_at(o, 8) - 1]; m1 = xs[ring_at(o, 8)]; m2 = xs[ring_at(o, 8) + 1];
+            } else {
+                u0 = xs[ring_at(o, 11) - 1]; u1 = xs[ring_at(o, 11)]; u2 = xs[ring_at(o, 11) + 1];
+                m0 = xs[ring_at(o, 12) - 1]; m1 = xs[ring_at(o, 12)]; m2 = xs[ring_at(o, 12) + 1];
+            }
+            float f_lap = 0.0f, f_lap2 = 0.0f, f_abs = 0.0f, f_g = 0.0f, f_g2 = 0.0f;
+            const int yr0 = B * SR + 4 * rg;
+            float* gp = FULL ? gdst + (size_t)(yb0 + yr0) * d.w + gxo : nullptr;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int rn = rg == 0 ? ring_at(o, 9 + jj) : ring_at(o, 13 + jj);
+                const double n0 = xs[rn - 1], n1 = xs[rn], n2 = xs[rn + 1];
+                const bool valid = colok && yr0 + jj < bh;
+                // scipy.ndimage.convolve: exact double accumulation, one rounding to float32
+                const float lap = (float)(4.0 * m1 - u1 - m0 - m2 - n1);
+                const float sh = (float)(0.25 * (u0 - n0) + 0.5 * (u1 - n1) + 0.25 * (u2 - n2));
+                const float sv = (float)(0.25 * (u0 - u2) + 0.5 * (m0 - m2) + 0.25 * (n0 - n2));
+                const float g = sqrt_rn_fast(__fadd_rn(__fmul_rn(sh, sh), __fmul_rn(sv, sv)));
+                const float lapv = valid ? lap : 0.0f, gv = valid ? g : 0.0f;
+                f_lap += lapv;
+                f_lap2 = fmaf(lapv, lapv, f_lap2);
+                f_abs += fabsf(lapv);
+                f_g += gv;
+                f_g2 = fmaf(gv, gv, f_g2);
+                if (FULL) {
+                    const float xc = slow ? (float)m1 : f32_bits_of(m1);
+                    const double xv = valid ? m1 : 0.0;
+                    if (valid) gp[(size_t)jj * d.w] = g;
+                    gmax = fmaxf(gmax, gv);
+                    a_x += xv;
+                    a_x2 = fma(xv, xv, a_x2);
+                    c_low += (valid && xc <= 0.01f);
+                    c_high += (valid && xc >= 0.99f);
+                    hist_add3(sm.h256, bin256_fp(xc), valid && xc >= 0.0f && xc <= 1.0f, sm.hx, bin1_fp(xc),
+                              sm.hg, bin1_fp(g), valid, lane);
+                }
+                u0 = m0; u1 = m1; u2 = m2;
+                m0 = n0; m1 = n1; m2 = n2;
+            }
+            a_lap += (double)f_lap; a_lap2 += (double)f_lap2; a_abs += (double)f_abs;
+            a_g += (double)f_g; a_g2 += (double)f_g2;
+        }
+        __syncthreads();
+        const int t = o.o0; o.o0 = o.o1; o.o1 = o.o2; o.o2 = t;
+    }
+
+    const bool k16 = wid < 4;
+    double v[NACC] = {a_x, a_x2, a_lap, a_lap2, a_abs, a_g, a_g2, k16 ? 0.0 : a_b1, k16 ? 0.0 : a_b2,
+                      k16 ? a_b1 : 0.0, k16 ? a_b2 : 0.0};
+    block_sum<NACC>(v, sm.red);
+    MetAcc* A = acc + si;
+    if (FULL) {
+        const unsigned cl = warp_sum_u(c_low), ch = warp_sum_u(c_high);
+        const float gm = warp_max(gmax);
+        if (lane == 0) {
+            if (cl) atomicAdd(&A->cnt_low, (unsigned long long)cl);
+            if (ch) atomicAdd(&A->cnt_high, (unsigned long long)ch);
+            atomicMax(&A->gmax_key, f2key(gm));
+        }
+    }
+    if (tid == 0) {
+        if (FULL) {
+            atomicAdd(&A->sum_x, v[0]); atomicAdd(&A->sum_x2, v[1]);
+            atomicAdd(&A->sum_lap, v[2]); atomicAdd(&A->sum_lap2, v[3]);
+            atomicAdd(&A->sum_g2, v[6]); atomicAdd(&A->sum_ls, v[7]); atomicAdd(&A->sum_ls2, v[8]);
+        }
+        atomicAdd(&A->sum_abslap, v[4]); atomicAdd(&A->sum_g, v[5]);
+        if (want16) { atomicAdd(&A->box16[0], v[9]); atomicAdd(&A->box16[1], v[10]); }
+    }
+    if (FULL) {
+        for (int i = tid; i < 256; i += NT) { unsigned c = sm.h256[i]; if (c) atomicAdd(&A->hist256[i], c); }
+        unsigned* gx_ = l1x + (size_t)si * SEL_L1_BINS;
+        unsigned* gg_ = l1g + (size_t)si * SEL_L1_BINS;
+        for (int i = tid; i < SEL_L1_BINS; i += NT) {
+            unsigned c = sm.hx[i]; if (c) atomicAdd(&gx_[i], c);
+            unsigned u = sm.hg[i]; if (u) atomicAdd(&gg_[i], u);
+        }
+    }
+}
+
+// rows per band: whole strips when the batch alone fills the machine, shorter bands (15 warm-up
+// rows each) for small batches
+inline int band_rows(int n_sel, int h, int w) {
+    const int strips = (w + SW - 1) / SW;
+    const long long want = 4LL * 148 * 2;                  // ~4 waves of 2 blocks per SM
+    long long bands = (want + (long long)strips * n_sel - 1) / ((long long)strips * n_sel);
+    const int max_bands = (h + 63) / 64;                   // at least 64 rows per band
+    if (bands > max_bands) bands = max_bands;
+    if (bands < 1) bands = 1;
+    int bh = (int)((h + bands - 1) / bands);
+    bh = (bh + SR - 1) / SR * SR;
+    return bh;
+}
+
+template <bool FULL>
+void launch(const float* img, const Dims& d, int want16, MetAcc* acc, float* gout, unsigned* l1x, unsigned* l1g,
+            cudaStream_t stream) {
+    static unsigned long long devices_done = 0;
+    opt_in_shared_memory(k_strip_stats<FULL>, sizeof(Smem), devices_done);
+    const int bh = band_rows(d.n_sel, d.h, d.w);
+    const int strips = (d.w + SW - 1) / SW, bands = (d.h + bh - 1) / bh;
+    MDIMG_LAUNCH k_strip_stats<FULL><<<dim3(strips * bands, d.n_sel), NT, sizeof(Smem), stream>>>(
+        img, d, bh, want16, acc, gout, l1x, l1g);
+}
+
+}  // namespace strip
+
 // Light variant for the halo guard / NIQE: only sum|laplace| and sum|grad|.
 constexpr int EW = 64, EH = 32, EXW = EW + 2, EXH = EH + 2, EXP = EXW + 1;
 
@@ -412,7 +781,7 @@ k_grad_pass(const float* __restrict__ gbuf, Dims d, const GradPrep* __restrict__
     const GradPrep& P = prep[si];
     for (int i = tid; i < 129; i += NT) edges[i] = P.edges[i];
     for (int i = tid; i < 128; i += NT) h[i] = 0;
-    const float denom = P.denom, last = P.last, thr = P.thr_edge, t90 = P.t90;
+    const float scale = __fdiv_rn(128.0f, P.denom), last = P.last, thr = P.thr_edge, t90 = P.t90;
     __syncthreads();
     const float* g = gbuf + (size_t)s * d.h * d.w;
     const int len = d.h * d.w;
@@ -422,9 +791,12 @@ k_grad_pass(const float* __restrict__ gbuf, Dims d, const GradPrep* __restrict__
         c_edge += (ok && v > thr);
         if (ok && v >= t90) { c_strong++; s_strong[0] += (double)v; }
         const bool in = ok && v >= 0.0f && v <= last;
-        int b = (int)__fmul_rn(__fdiv_rn(v, denom), 128.0f);
+        // numpy: tentative bin int((v / denom) * 128), then corrected against the float32 edge array by at
+        // most one bin either way -- the bin is DEFINED by the edges, so any tentative index within one bin
+        // of it gives numpy's result; a multiply by the reciprocal replaces the IEEE division
+        int b = (int)__fmul_rn(v, scale);
         b = min(max(b, 0), 127);
-        if (v < edges[b]) b -= 1;                 // numpy corrects the tentative bin against the edge array
+        if (v < edges[b]) b -= 1;
         else if (b != 127 && v >= edges[b + 1]) b += 1;
         b = min(max(b, 0), 127);
         hist_add(h, b, in, lane);                 // warp-uniform fast path for flat regions
@@ -566,11 +938,26 @@ __global__ void k_quality_out(Dims d, const double* __restrict__ edge2, const do
     }
 }
 
+__global__ void k_quality_gather(int n_sel, const MetAcc* __restrict__ acc, double* __restrict__ edge2,
+                                 double* __restrict__ box2) {
+    int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= n_sel) return;
+    edge2[si * 2] = acc[si].sum_abslap;
+    edge2[si * 2 + 1] = acc[si].sum_g;
+    box2[si * 2] = acc[si].box16[0];
+    box2[si * 2 + 1] = acc[si].box16[1];
+}
+
 __global__ void k_copy_box16(int n_sel, const double* __restrict__ box2, MetAcc* __restrict__ acc) {
     int si = blockIdx.x * blockDim.x + threadIdx.x;
     if (si >= n_sel) return;
     acc[si].box16[0] = box2[si * 2];
     acc[si].box16[1] = box2[si * 2 + 1];
+}
+
+bool legacy_tiles() {
+    static const bool v = [] { const char* e = getenv("MDIMG_METRICS_TILES"); return e && e[0] == '1'; }();
+    return v;
 }
 
 struct SigmaBufs {
@@ -644,6 +1031,7 @@ size_t quality_workspace_bytes(int n_sel, int h, int w) {
     Arena a(nullptr, 0);
     a.take<double>((size_t)n_sel * 2);
     a.take<double>((size_t)n_sel * 2);
+    a.take<MetAcc>(n_sel);
     return a.off;
 }
 
@@ -653,12 +1041,20 @@ int quality_run(const float* img, const Dims& d, int flags, double* out, void* w
     Arena a(ws, ws_bytes);
     double* edge2 = a.take<double>((size_t)d.n_sel * 2);
     double* box2 = a.take<double>((size_t)d.n_sel * 2);
+    MetAcc* acc = a.take<MetAcc>(d.n_sel);
     if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "quality: workspace too small");
-    cudaMemsetAsync(edge2, 0, sizeof(double) * 2 * d.n_sel, stream);
-    cudaMemsetAsync(box2, 0, sizeof(double) * 2 * d.n_sel, stream);
-    dim3 grid(((d.w + EW - 1) / EW) * ((d.h + EH - 1) / EH), d.n_sel);
-    MDIMG_LAUNCH k_edge_stats<<<grid, NT, 0, stream>>>(img, d, edge2);
-    if (flags & 1) launch_box16_stats(img, d, box2, stream);
+    if (legacy_tiles()) {
+        cudaMemsetAsync(edge2, 0, sizeof(double) * 2 * d.n_sel, stream);
+        cudaMemsetAsync(box2, 0, sizeof(double) * 2 * d.n_sel, stream);
+        dim3 grid(((d.w + EW - 1) / EW) * ((d.h + EH - 1) / EH), d.n_sel);
+        MDIMG_LAUNCH k_edge_stats<<<grid, NT, 0, stream>>>(img, d, edge2);
+        if (flags & 1) launch_box16_stats(img, d, box2, stream);
+    } else {
+        // the strip kernel without histograms / 7-window / |grad| store: sum|laplace|, sum|grad|, 16-window stats
+        cudaMemsetAsync(acc, 0, sizeof(MetAcc) * d.n_sel, stream);
+        strip::launch<false>(img, d, flags & 1, acc, nullptr, nullptr, nullptr, stream);
+        MDIMG_LAUNCH k_quality_gather<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d.n_sel, acc, edge2, box2);
+    }
     MDIMG_LAUNCH k_quality_out<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, edge2, box2, flags, out);
     return check_launch("quality");
 }
@@ -709,10 +1105,17 @@ int metrics_run(const float* img, const Dims& d, const PctPlan& plan, int flags,
     cudaMemsetAsync(m.l1x, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
     cudaMemsetAsync(m.l1g, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
 
-    static unsigned long long devices_done = 0;
-    opt_in_shared_memory(k_stencil_stats, sizeof(StencilSmem), devices_done);
-    dim3 grid(((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH), d.n_sel);
-    MDIMG_LAUNCH k_stencil_stats<<<grid, NT, sizeof(StencilSmem), stream>>>(img, d, m.acc, m.g, m.l1x, m.l1g);
+    // one read of the image: stencil statistics, |grad|, both box filters, histograms (flags bit0: the
+    // 16x16 NIQE window too).  MDIMG_METRICS_TILES=1 selects the previous tile kernels (A/B measurements).
+    const bool tiles = legacy_tiles();
+    if (tiles) {
+        static unsigned long long devices_done = 0;
+        opt_in_shared_memory(k_stencil_stats, sizeof(StencilSmem), devices_done);
+        dim3 grid(((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH), d.n_sel);
+        MDIMG_LAUNCH k_stencil_stats<<<grid, NT, sizeof(StencilSmem), stream>>>(img, d, m.acc, m.g, m.l1x, m.l1g);
+    } else {
+        strip::launch<true>(img, d, flags & 1, m.acc, m.g, m.l1x, m.l1g, stream);
+    }
     int rc = check_launch("stencil_stats");
     if (rc) return rc;
 
@@ -742,7 +1145,7 @@ int metrics_run(const float* img, const Dims& d, const PctPlan& plan, int flags,
     if (bx > 512) bx = 512;
     MDIMG_LAUNCH k_grad_pass<<<dim3(bx, d.n_sel), NT, 0, stream>>>(m.g, d, m.prep, m.acc);
 
-    if (flags & 1) {
+    if ((flags & 1) && tiles) {
         cudaMemsetAsync(m.box2, 0, sizeof(double) * 2 * d.n_sel, stream);
         launch_box16_stats(img, d, m.box2, stream);
         MDIMG_LAUNCH k_copy_box16<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d.n_sel, m.box2, m.acc);

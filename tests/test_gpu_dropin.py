@@ -609,3 +609,28 @@ def test_concurrent_callers_get_the_serial_results(api, synth):
     for (e0, l0, m0, s0), (e1, l1, m1, s1) in zip(serial, results):
         np.testing.assert_array_equal(e0, e1)
         assert l0 == l1 and m0 == m1 and s0 == s1
+
+
+def test_process_cohort_single_rank_equals_the_stack_pipeline(ops, synth, tmp_path, monkeypatch):
+    """shard.process_cohort without a process group (world 1): device volumes and host volumes give the rows of
+    batch.process_stack, the gathered rows stay on the device, and `persist` writes one run per slice."""
+    import torch
+    from mdimg_b200.batch import PACK_COLS, process_stack
+    from mdimg_b200.pipeline import storage
+    from mdimg_b200.shard import process_cohort
+    monkeypatch.setenv("MDIMG_DB_PATH", str(tmp_path / "cohort.db"))
+    plan = synth.plan_full()
+    vols = [np.stack([synth.ct_slice(6000 + 10 * v + z, z / 3, size=96) for z in range(n)]) for v, n in enumerate((3, 2))]
+    dev_vols = [torch.from_numpy(v.view(np.int16)).to(ops.device) for v in vols]
+    res = process_cohort(dev_vols, plan, chunk=2, ops=ops, persist={"input_filename": "cohort.npy"})
+    assert res.rows.is_cuda and tuple(res.rows.shape) == (5, PACK_COLS) and res.counts == [5]
+    want = np.concatenate([process_stack(d, plan, chunk=2, ops=ops).packed for d in dev_vols])
+    np.testing.assert_allclose(res.rows_host(), want, rtol=1e-9, atol=1e-12)
+    assert [(v, a, b) for v, a, b, _, _ in res.local] == [(0, 0, 3), (1, 0, 2)]
+    assert len(res.run_ids) == 5 and len(res.labels) == 5
+    runs = storage.list_runs(limit=10)
+    assert len(runs) == 5 and {r["run_id"] for r in runs} == set(res.run_ids)
+    host = process_cohort(vols, plan, chunk=2, ops=ops)
+    np.testing.assert_allclose(host.rows_host(), want, rtol=1e-9, atol=1e-12)
+    for (v, a, b, enh_h, _), (_, _, _, enh_d, _) in zip(host.local, res.local):
+        np.testing.assert_array_equal(enh_h, enh_d.cpu().numpy())

@@ -70,6 +70,11 @@ const char* mdimg_last_error(void);
 int mdimg_version(void);
 /* Number of CUDA kernels this library has launched in this process (all threads). */
 unsigned long long mdimg_launch_count(void);
+/* Device self-test of mdimg_normalize_u16's quotient: (a - min) / (max - min) is evaluated with the slice's
+ * correctly rounded reciprocal and one exact-residual correction instead of an IEEE division per pixel; this
+ * runs both over EVERY integer operand pair 0 <= a <= denom <= 65535 and writes the number of differing
+ * results (must be 0) to *mismatches (host pointer).  Synchronises `stream`. */
+int mdimg_selftest_div16(unsigned long long* mismatches, void* stream);
 
 /* Select the device and verify it is compute capability 10.x (B200). */
 int mdimg_init(int device);

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "mdimg_last_error": (C.c_char_p, []),
     "mdimg_version": (_i, []),
     "mdimg_launch_count": (C.c_ulonglong, []),
+    "mdimg_selftest_div16": (_i, [C.POINTER(C.c_ulonglong), _p]),
     "mdimg_init": (_i, [_i]),
     "mdimg_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
     "mdimg_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -82,6 +82,18 @@ int mdimg_version(void) { return 100; }
 
 unsigned long long mdimg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int mdimg_selftest_div16(unsigned long long* mismatches, void* stream) {
+    if (!mismatches) return set_error(MDIMG_ERR_INVALID, "selftest: null result pointer");
+    unsigned long long* dev = nullptr;
+    if (cudaMalloc(&dev, sizeof(*dev)) != cudaSuccess) return set_error(MDIMG_ERR_CUDA, "selftest: cudaMalloc failed");
+    int rc = selftest_div16_run(dev, (cudaStream_t)stream);
+    if (!rc && cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess)
+        rc = set_error(MDIMG_ERR_CUDA, "selftest: copy failed");
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(dev);
+    return rc;
+}
+
 int mdimg_init(int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);

@@ -14,6 +14,8 @@ int minmax_decode_run(const uint2* mm, const Dims& d, float* out2, cudaStream_t 
 // normalize_image (pipeline/dicom_io.py:84-91)
 int normalize_u16_run(const uint16_t* in, float* out, const Dims& d, const uint2* mm, cudaStream_t stream);
 int normalize_f32_run(const float* in, float* out, const Dims& d, const uint2* mm, cudaStream_t stream);
+// Exhaustive device check of the normalise quotient (see div16 in pointwise.cu); *mismatches_dev receives the count.
+int selftest_div16_run(unsigned long long* mismatches_dev, cudaStream_t stream);
 // load_dicom's pixel path (modality rescale, MONOCHROME1 inversion) fused with normalize_image.
 // mm: device [n] uint2 scratch, gmm: device [1] uint2 scratch.
 int ingest_run(const uint16_t* in, float* out, const Dims& d, double slope, double intercept,

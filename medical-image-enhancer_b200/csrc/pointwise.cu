@@ -55,6 +55,51 @@ k_minmax(const T* __restrict__ img, Dims d, uint2* __restrict__ mm) {
     }
 }
 
+// uint16 samples: 128-bit loads (8 samples), four in flight per thread, packed 16-bit min / max; the
+// float keys are formed once per block.  Streams 2 B/px at HBM speed (the scalar version above moved
+// 64 bytes per warp instruction).
+__global__ void __launch_bounds__(NT)
+k_minmax_u16v(const uint16_t* __restrict__ img, Dims d, uint2* __restrict__ mm) {
+    __shared__ unsigned smin[NT / 32], smax[NT / 32];
+    const int s = slice_of(d.sel, blockIdx.y);
+    const long long len = d.px();
+    const uint16_t* p = img + (size_t)s * len;
+    unsigned lo2 = 0xFFFFFFFFu, hi2 = 0u;                 // two 16-bit lanes each
+    auto take = [&](const uint4& v) {
+        lo2 = __vminu2(__vminu2(lo2, v.x), __vminu2(v.y, __vminu2(v.z, v.w)));
+        hi2 = __vmaxu2(__vmaxu2(hi2, v.x), __vmaxu2(v.y, __vmaxu2(v.z, v.w)));
+    };
+    const long long tid0 = (long long)blockIdx.x * NT + threadIdx.x, nthr = (long long)gridDim.x * NT;
+    long long done = 0;
+    if ((((uintptr_t)p) & 15) == 0) {
+        const long long n8 = len >> 3;
+        const uint4* p8 = reinterpret_cast<const uint4*>(p);
+        long long i = tid0;
+        for (; i + 3 * nthr < n8; i += 4 * nthr) {
+            const uint4 a = __ldg(p8 + i), b = __ldg(p8 + i + nthr), c = __ldg(p8 + i + 2 * nthr), e = __ldg(p8 + i + 3 * nthr);
+            take(a); take(b); take(c); take(e);
+        }
+        for (; i < n8; i += nthr) take(__ldg(p8 + i));
+        done = n8 << 3;
+    }
+    unsigned lo = min(lo2 & 0xffffu, lo2 >> 16), hi = max(hi2 & 0xffffu, hi2 >> 16);
+    for (long long i = done + tid0; i < len; i += nthr) {
+        const unsigned v = p[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { smin[wid] = lo; smax[wid] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < NT / 32; ++w) { lo = min(lo, smin[w]); hi = max(hi, smax[w]); }
+        atomicMin(&mm[s].x, f2key((float)lo));
+        atomicMax(&mm[s].y, f2key((float)hi));
+    }
+}
+
 __global__ void k_mm_decode(Dims d, const uint2* __restrict__ mm, float* __restrict__ out2) {
     int si = blockIdx.x * blockDim.x + threadIdx.x;
     if (si >= d.n_sel) return;
@@ -110,30 +155,68 @@ struct NormF {
     }
 };
 
+// (a - lo) / denom for INTEGER operands 0 <= a <= denom <= 65535 (uint16 samples minus the slice minimum
+// over max - min): the IEEE quotient from the slice's correctly rounded reciprocal and one exact-residual
+// correction -- q = a * r; q += fma(-denom, q, a) * r -- i.e. 3 FP32-pipe instructions per pixel instead
+// of the ~10-instruction division sequence with its MUFU.  Markstein's correction step; that it equals
+// __fdiv_rn for EVERY operand pair of this domain is checked exhaustively on the device
+// (mdimg_selftest_div16, tests/test_gpu_parity.py).
+__device__ __forceinline__ float div16(float a, float denom, float rcp) {
+    const float q = __fmul_rn(a, rcp);
+    return __fmaf_rn(__fmaf_rn(-denom, q, a), rcp, q);
+}
+
 __global__ void __launch_bounds__(NT)
 k_normalize_u16(const uint16_t* __restrict__ in, float* __restrict__ out, Dims d,
                 const uint2* __restrict__ mm) {
     const int s = slice_of(d.sel, blockIdx.y);
     NormF f; f.mm = mm; f.prepare(s);
+    const float lo = f.lo, denom = f.denom;
+    const bool zero = f.zero;
+    const float rcp = zero ? 0.0f : __frcp_rn(denom);
     const long long len = d.px();
     const uint16_t* p = in + (size_t)s * len;
     float* o = out + (size_t)s * len;
-    const bool aligned = (((uintptr_t)p & 7) == 0) && (((uintptr_t)o & 15) == 0);
-    if ((len & 3) == 0 && aligned) {
-        const long long n4 = len >> 2;
-        const ushort4* p4 = reinterpret_cast<const ushort4*>(p);
+    auto one = [&](unsigned u) { return zero ? 0.0f : div16(__fsub_rn((float)u, lo), denom, rcp); };
+    const long long tid0 = (long long)blockIdx.x * NT + threadIdx.x, nthr = (long long)gridDim.x * NT;
+    long long done = 0;
+    if (((((uintptr_t)p) | ((uintptr_t)o)) & 15) == 0) {
+        const long long n8 = len >> 3;
+        const uint4* p8 = reinterpret_cast<const uint4*>(p);
         float4* o4 = reinterpret_cast<float4*>(o);
-        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
-            ushort4 v = p4[i];
-            float4 r;
-            r.x = f.apply((float)v.x, 0); r.y = f.apply((float)v.y, 0);
-            r.z = f.apply((float)v.z, 0); r.w = f.apply((float)v.w, 0);
-            o4[i] = r;
+        auto emit = [&](long long i, const uint4& v) {
+            float4 a, b;
+            a.x = one(v.x & 0xffffu); a.y = one(v.x >> 16); a.z = one(v.y & 0xffffu); a.w = one(v.y >> 16);
+            b.x = one(v.z & 0xffffu); b.y = one(v.z >> 16); b.z = one(v.w & 0xffffu); b.w = one(v.w >> 16);
+            __stcs(o4 + 2 * i, a);
+            __stcs(o4 + 2 * i + 1, b);
+        };
+        long long i = tid0;
+        for (; i + nthr < n8; i += 2 * nthr) {           // two 128-bit loads in flight
+            const uint4 v0 = __ldg(p8 + i), v1 = __ldg(p8 + i + nthr);
+            emit(i, v0);
+            emit(i + nthr, v1);
         }
-    } else {
-        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < len; i += (long long)gridDim.x * NT)
-            o[i] = f.apply((float)p[i], 0);
+        for (; i < n8; i += nthr) emit(i, __ldg(p8 + i));
+        done = n8 << 3;
     }
+    for (long long i = done + tid0; i < len; i += nthr) o[i] = one(p[i]);
+}
+
+// Exhaustive check of div16 against the IEEE division over its whole domain: denom = blockIdx-strided
+// 1 .. 65535, a = 0 .. denom.  mismatches: device counter.
+__global__ void __launch_bounds__(NT)
+k_selftest_div16(unsigned long long* __restrict__ mismatches) {
+    unsigned bad = 0;
+    for (unsigned dn = 1 + blockIdx.x; dn <= 65535u; dn += gridDim.x) {
+        const float denom = (float)dn, rcp = __frcp_rn(denom);
+        for (unsigned a = threadIdx.x; a <= dn; a += NT) {
+            const float fa = (float)a;
+            bad += __float_as_uint(div16(fa, denom, rcp)) != __float_as_uint(__fdiv_rn(fa, denom));
+        }
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);
 }
 
 // ---- ingestion: modality rescale + MONOCHROME1 inversion + normalize_image in one pass --------
@@ -260,7 +343,7 @@ int minmax_f32_run(const float* img, const Dims& d, uint2* mm, cudaStream_t stre
 int minmax_u16_run(const uint16_t* img, const Dims& d, uint2* mm, cudaStream_t stream) {
     if (d.n_sel == 0) return MDIMG_OK;
     MDIMG_LAUNCH k_mm_init<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, mm);
-    MDIMG_LAUNCH k_minmax<uint16_t><<<dim3(blocks_for(d.px(), 16), d.n_sel), NT, 0, stream>>>(img, d, mm);
+    MDIMG_LAUNCH k_minmax_u16v<<<dim3(blocks_for(d.px(), 64), d.n_sel), NT, 0, stream>>>(img, d, mm);
     return check_launch("minmax_u16");
 }
 
@@ -271,7 +354,7 @@ int ingest_run(const uint16_t* in, float* out, const Dims& d, double slope, doub
     if (is_signed)
         MDIMG_LAUNCH k_minmax<short><<<dim3(blocks_for(d.px(), 16), d.n_sel), NT, 0, stream>>>((const short*)in, d, mm);
     else
-        MDIMG_LAUNCH k_minmax<uint16_t><<<dim3(blocks_for(d.px(), 16), d.n_sel), NT, 0, stream>>>(in, d, mm);
+        MDIMG_LAUNCH k_minmax_u16v<<<dim3(blocks_for(d.px(), 64), d.n_sel), NT, 0, stream>>>(in, d, mm);
     MDIMG_LAUNCH k_global_mm<<<1, 256, 0, stream>>>(d.n_sel, d, mm, gmm);
     IngestParams P;
     P.slope = slope; P.intercept = intercept; P.has_rescale = has_rescale; P.invert = invert; P.is_signed = is_signed;
@@ -287,8 +370,14 @@ int minmax_decode_run(const uint2* mm, const Dims& d, float* out2, cudaStream_t 
 
 int normalize_u16_run(const uint16_t* in, float* out, const Dims& d, const uint2* mm, cudaStream_t stream) {
     if (d.n_sel == 0) return MDIMG_OK;
-    MDIMG_LAUNCH k_normalize_u16<<<dim3(blocks_for(d.px(), 8), d.n_sel), NT, 0, stream>>>(in, out, d, mm);
+    MDIMG_LAUNCH k_normalize_u16<<<dim3(blocks_for(d.px(), 32), d.n_sel), NT, 0, stream>>>(in, out, d, mm);
     return check_launch("normalize_u16");
+}
+
+int selftest_div16_run(unsigned long long* mismatches_dev, cudaStream_t stream) {
+    cudaMemsetAsync(mismatches_dev, 0, sizeof(unsigned long long), stream);
+    MDIMG_LAUNCH k_selftest_div16<<<148 * 8, NT, 0, stream>>>(mismatches_dev);
+    return check_launch("selftest_div16");
 }
 
 int normalize_f32_run(const float* in, float* out, const Dims& d, const uint2* mm, cudaStream_t stream) {

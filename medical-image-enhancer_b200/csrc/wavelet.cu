@@ -16,6 +16,7 @@
 #include "enhance.cuh"
 #include "select.cuh"
 
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -54,7 +55,7 @@ Pyramid make_pyramid(int h, int w) {
         p.off[l] = o;
         o += 3LL * p.H[l] * p.W[l];
     }
-    p.det_per_slice = o;
+    p.det_per_slice = (o + 3) & ~3LL;          // slices start 16-byte aligned (128-bit coefficient accesses)
     p.a_cap = (long long)p.H[1] * p.W[1];
     p.r_cap = (long long)(p.H[1] + 2) * (p.W[1] + 2);
     return p;
@@ -125,6 +126,102 @@ k_haar_fwd(const float* __restrict__ in, long long in_stride, int h0, int w0, Di
         __syncthreads();
         unsigned* g = l1 + (size_t)si * SEL_L1_BINS;
         for (int i = threadIdx.x; i < SEL_L1_BINS; i += NT) { unsigned v = hh[i]; if (v) atomicAdd(&g[i], v); }
+    }
+}
+
+// ---- fused forward levels 1..3 ---------------------------------------------------------------
+// For extents divisible by 8 every 8 x 8 pixel block is an independent 3-level Haar pyramid (SURVEY 8c
+// item 5).  ONE THREAD owns a block: it loads its 64 pixels (128-bit loads), runs levels 1-3 entirely in
+// registers with the arithmetic of k_haar_fwd, and stores the detail coefficients of the three levels
+// (4 / 2 / 1 consecutive values per band row: 128- / 64- / 32-bit stores, contiguous across the warp) and
+// its level-3 approximation, where the per-level kernels continue on 1/64 of the data.  No shared
+// memory, no barrier, one read of the image and one write of the coefficients.
+struct Haar4 { float aa, ad, da, dd; };
+__device__ __forceinline__ Haar4 haar_fwd_2x2(float v00, float v01, float v10, float v11) {
+    const float S = (float)SQ, NS = -(float)SQ;
+    // axis 0, then axis 1 (pywt: out[o] = f[0] * x[2o + 1] + f[1] * x[2o], float32)
+    const float lo0 = __fadd_rn(__fmul_rn(S, v10), __fmul_rn(S, v00));
+    const float lo1 = __fadd_rn(__fmul_rn(S, v11), __fmul_rn(S, v01));
+    const float hi0 = __fadd_rn(__fmul_rn(NS, v10), __fmul_rn(S, v00));
+    const float hi1 = __fadd_rn(__fmul_rn(NS, v11), __fmul_rn(S, v01));
+    Haar4 r;
+    r.aa = __fadd_rn(__fmul_rn(S, lo1), __fmul_rn(S, lo0));
+    r.ad = __fadd_rn(__fmul_rn(NS, lo1), __fmul_rn(S, lo0));
+    r.da = __fadd_rn(__fmul_rn(S, hi1), __fmul_rn(S, hi0));
+    r.dd = __fadd_rn(__fmul_rn(NS, hi1), __fmul_rn(S, hi0));
+    return r;
+}
+
+__global__ void __launch_bounds__(NT)
+k_haar_fwd_reg3(const float* __restrict__ in, Dims d, const int* __restrict__ skip, Pyramid p,
+                float* __restrict__ aout, float* __restrict__ det, WaveAcc* __restrict__ acc,
+                unsigned* __restrict__ l1, int want_hist) {
+    __shared__ unsigned hh[SEL_L1_BINS];
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    if (skip && skip[s]) return;
+    const int tid = threadIdx.x;
+    if (want_hist) {
+        for (int i = tid; i < SEL_L1_BINS; i += NT) hh[i] = 0;
+        __syncthreads();
+    }
+    const int bw = d.w >> 3, nblk = (d.h >> 3) * bw;
+    const float* src = in + (size_t)s * d.h * d.w;
+    float* db = det + (size_t)si * p.det_per_slice;
+    const int W1 = p.W[1], W2 = p.W[2], W3 = p.W[3];
+    const long long band1 = (long long)p.H[1] * W1, band2 = (long long)p.H[2] * W2, band3 = (long long)p.H[3] * W3;
+    float* d1 = db + p.off[1];
+    float* d2 = db + p.off[2];
+    float* d3 = db + p.off[3];
+    float* a3 = aout + (size_t)si * p.a_cap;
+    unsigned nz = 0;
+    for (int b = blockIdx.x * NT + tid; b < nblk; b += gridDim.x * NT) {
+        const int by = b / bw, bx = b - by * bw;
+        const float* blk = src + (size_t)(8 * by) * d.w + 8 * bx;
+        float a1[4][4];                                   // level-1 approximations of the block
+#pragma unroll
+        for (int yy = 0; yy < 4; ++yy) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(blk + (size_t)(2 * yy) * d.w));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(blk + (size_t)(2 * yy) * d.w) + 1);
+            const float4 u0 = __ldg(reinterpret_cast<const float4*>(blk + (size_t)(2 * yy + 1) * d.w));
+            const float4 u1 = __ldg(reinterpret_cast<const float4*>(blk + (size_t)(2 * yy + 1) * d.w) + 1);
+            const Haar4 c0 = haar_fwd_2x2(t0.x, t0.y, u0.x, u0.y), c1 = haar_fwd_2x2(t0.z, t0.w, u0.z, u0.w);
+            const Haar4 c2 = haar_fwd_2x2(t1.x, t1.y, u1.x, u1.y), c3 = haar_fwd_2x2(t1.z, t1.w, u1.z, u1.w);
+            a1[yy][0] = c0.aa; a1[yy][1] = c1.aa; a1[yy][2] = c2.aa; a1[yy][3] = c3.aa;
+            const size_t o = (size_t)(4 * by + yy) * W1 + 4 * bx;
+            *reinterpret_cast<float4*>(d1 + o) = make_float4(c0.ad, c1.ad, c2.ad, c3.ad);
+            *reinterpret_cast<float4*>(d1 + band1 + o) = make_float4(c0.da, c1.da, c2.da, c3.da);
+            *reinterpret_cast<float4*>(d1 + 2 * band1 + o) = make_float4(c0.dd, c1.dd, c2.dd, c3.dd);
+            if (want_hist) {
+                const float e[4] = {fabsf(c0.dd), fabsf(c1.dd), fabsf(c2.dd), fabsf(c3.dd)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { nz += (e[k] == 0.0f); atomicAdd(&hh[sel_bin1(e[k])], 1u); }
+            }
+        }
+        float a2[2][2];
+#pragma unroll
+        for (int yy = 0; yy < 2; ++yy) {
+            const Haar4 c0 = haar_fwd_2x2(a1[2 * yy][0], a1[2 * yy][1], a1[2 * yy + 1][0], a1[2 * yy + 1][1]);
+            const Haar4 c1 = haar_fwd_2x2(a1[2 * yy][2], a1[2 * yy][3], a1[2 * yy + 1][2], a1[2 * yy + 1][3]);
+            a2[yy][0] = c0.aa; a2[yy][1] = c1.aa;
+            const size_t o = (size_t)(2 * by + yy) * W2 + 2 * bx;
+            *reinterpret_cast<float2*>(d2 + o) = make_float2(c0.ad, c1.ad);
+            *reinterpret_cast<float2*>(d2 + band2 + o) = make_float2(c0.da, c1.da);
+            *reinterpret_cast<float2*>(d2 + 2 * band2 + o) = make_float2(c0.dd, c1.dd);
+        }
+        const Haar4 c = haar_fwd_2x2(a2[0][0], a2[0][1], a2[1][0], a2[1][1]);
+        const size_t o3 = (size_t)by * W3 + bx;
+        d3[o3] = c.ad;
+        d3[band3 + o3] = c.da;
+        d3[2 * band3 + o3] = c.dd;
+        a3[o3] = c.aa;
+    }
+    if (want_hist) {
+        nz = warp_sum_u(nz);
+        if ((tid & 31) == 0 && nz) atomicAdd(&acc[si].dd_zero, nz);
+        __syncthreads();
+        unsigned* g = l1 + (size_t)si * SEL_L1_BINS;
+        for (int i = tid; i < SEL_L1_BINS; i += NT) { unsigned v = hh[i]; if (v) atomicAdd(&g[i], v); }
     }
 }
 
@@ -410,6 +507,95 @@ k_haar_inv(const TA* __restrict__ ain, long long a_stride, int a_pitch, int hd, 
     }
 }
 
+// ---- fused inverse levels 3..1 ---------------------------------------------------------------
+// The counterpart of k_haar_fwd_reg3: a thread takes its level-3 approximation and the 63 detail
+// coefficients of its block (shrinkage fused into the loads), rebuilds levels 2 and 1 in registers with the
+// arithmetic of k_haar_inv and stores its 8 x 8 pixels of the float32 result (128-bit stores).
+template <typename T> struct Quad { T o00, o01, o10, o11; };
+template <typename T>
+__device__ __forceinline__ Quad<T> haar_inv_2x2(T aa, T ad, T da, T dd) {
+    typedef Ops<T> O;
+    const T S = (T)SQ, NS = -(T)SQ;
+    // axis 1: 'a' = idwt(aa, ad), 'd' = idwt(da, dd); then axis 0
+    const T a_e = O::add(O::mul(S, aa), O::mul(S, ad));
+    const T a_o = O::add(O::mul(S, aa), O::mul(NS, ad));
+    const T d_e = O::add(O::mul(S, da), O::mul(S, dd));
+    const T d_o = O::add(O::mul(S, da), O::mul(NS, dd));
+    Quad<T> q;
+    q.o00 = O::add(O::mul(S, a_e), O::mul(S, d_e));
+    q.o10 = O::add(O::mul(S, a_e), O::mul(NS, d_e));
+    q.o01 = O::add(O::mul(S, a_o), O::mul(S, d_o));
+    q.o11 = O::add(O::mul(S, a_o), O::mul(NS, d_o));
+    return q;
+}
+
+template <typename T, typename TA, int MODE>
+__global__ void __launch_bounds__(NT)
+k_haar_inv_reg3(const TA* __restrict__ ain, long long a_stride, int a_pitch, Dims d, const int* __restrict__ skip,
+                Pyramid p, const float* __restrict__ det, const WaveAcc* __restrict__ acc,
+                const float* __restrict__ img_in, float* __restrict__ img_out) {
+    const int si = blockIdx.y;
+    const int s = slice_of(d.sel, si);
+    const int tid = threadIdx.x;
+    float* dst = img_out + (size_t)s * d.h * d.w;
+    if (skip && skip[s]) {                          // untouched slice: copy through
+        const float* a = img_in + (size_t)s * d.h * d.w;
+        const long long len = d.px();
+        if (a != dst)
+            for (long long i = (long long)blockIdx.x * NT + tid; i < len; i += (long long)gridDim.x * NT) dst[i] = a[i];
+        return;
+    }
+    const int bw = d.w >> 3, nblk = (d.h >> 3) * bw;
+    const float* db = det + (size_t)si * p.det_per_slice;
+    const int W1 = p.W[1], W2 = p.W[2], W3 = p.W[3];
+    const long long band1 = (long long)p.H[1] * W1, band2 = (long long)p.H[2] * W2, band3 = (long long)p.H[3] * W3;
+    const float* d1 = db + p.off[1];
+    const float* d2 = db + p.off[2];
+    const float* d3 = db + p.off[3];
+    const WaveAcc& A = acc[si];
+    const double t1a = A.thr[1][0], t1b = A.thr[1][1], t1c = A.thr[1][2];
+    const double t2a = A.thr[2][0], t2b = A.thr[2][1], t2c = A.thr[2][2];
+    const double t3a = A.thr[3][0], t3b = A.thr[3][1], t3c = A.thr[3][2];
+    const TA* ap = ain + (size_t)si * a_stride;
+    for (int b = blockIdx.x * NT + tid; b < nblk; b += gridDim.x * NT) {
+        const int by = b / bw, bx = b - by * bw;
+        const size_t o3 = (size_t)by * W3 + bx;
+        const Quad<T> q3 = haar_inv_2x2<T>((T)ap[(size_t)by * a_pitch + bx], shrink<T, MODE>(d3[o3], t3a),
+                                           shrink<T, MODE>(d3[band3 + o3], t3b), shrink<T, MODE>(d3[2 * band3 + o3], t3c));
+        const T a2[2][2] = {{q3.o00, q3.o01}, {q3.o10, q3.o11}};
+        T a1[4][4];
+#pragma unroll
+        for (int yy = 0; yy < 2; ++yy) {
+            const size_t o = (size_t)(2 * by + yy) * W2 + 2 * bx;
+            const float2 ad = *reinterpret_cast<const float2*>(d2 + o);
+            const float2 da = *reinterpret_cast<const float2*>(d2 + band2 + o);
+            const float2 dd = *reinterpret_cast<const float2*>(d2 + 2 * band2 + o);
+            const Quad<T> qa = haar_inv_2x2<T>(a2[yy][0], shrink<T, MODE>(ad.x, t2a), shrink<T, MODE>(da.x, t2b), shrink<T, MODE>(dd.x, t2c));
+            const Quad<T> qb = haar_inv_2x2<T>(a2[yy][1], shrink<T, MODE>(ad.y, t2a), shrink<T, MODE>(da.y, t2b), shrink<T, MODE>(dd.y, t2c));
+            a1[2 * yy][0] = qa.o00; a1[2 * yy][1] = qa.o01; a1[2 * yy][2] = qb.o00; a1[2 * yy][3] = qb.o01;
+            a1[2 * yy + 1][0] = qa.o10; a1[2 * yy + 1][1] = qa.o11; a1[2 * yy + 1][2] = qb.o10; a1[2 * yy + 1][3] = qb.o11;
+        }
+        float* blk = dst + (size_t)(8 * by) * d.w + 8 * bx;
+#pragma unroll
+        for (int yy = 0; yy < 4; ++yy) {
+            const size_t o = (size_t)(4 * by + yy) * W1 + 4 * bx;
+            const float4 ad = *reinterpret_cast<const float4*>(d1 + o);
+            const float4 da = *reinterpret_cast<const float4*>(d1 + band1 + o);
+            const float4 dd = *reinterpret_cast<const float4*>(d1 + 2 * band1 + o);
+            const Quad<T> q0 = haar_inv_2x2<T>(a1[yy][0], shrink<T, MODE>(ad.x, t1a), shrink<T, MODE>(da.x, t1b), shrink<T, MODE>(dd.x, t1c));
+            const Quad<T> q1 = haar_inv_2x2<T>(a1[yy][1], shrink<T, MODE>(ad.y, t1a), shrink<T, MODE>(da.y, t1b), shrink<T, MODE>(dd.y, t1c));
+            const Quad<T> q2 = haar_inv_2x2<T>(a1[yy][2], shrink<T, MODE>(ad.z, t1a), shrink<T, MODE>(da.z, t1b), shrink<T, MODE>(dd.z, t1c));
+            const Quad<T> q3r = haar_inv_2x2<T>(a1[yy][3], shrink<T, MODE>(ad.w, t1a), shrink<T, MODE>(da.w, t1b), shrink<T, MODE>(dd.w, t1c));
+            float4* r0 = reinterpret_cast<float4*>(blk + (size_t)(2 * yy) * d.w);
+            float4* r1 = reinterpret_cast<float4*>(blk + (size_t)(2 * yy + 1) * d.w);
+            r0[0] = make_float4((float)q0.o00, (float)q0.o01, (float)q1.o00, (float)q1.o01);
+            r0[1] = make_float4((float)q2.o00, (float)q2.o01, (float)q3r.o00, (float)q3r.o01);
+            r1[0] = make_float4((float)q0.o10, (float)q0.o11, (float)q1.o10, (float)q1.o11);
+            r1[1] = make_float4((float)q2.o10, (float)q2.o11, (float)q3r.o10, (float)q3r.o11);
+        }
+    }
+}
+
 struct WaveBufs {
     WaveAcc* acc; float* det; float* a0; float* a1; double* r0; double* r1;
     unsigned* l1; int* ranks; float* med; void* sel_ws; size_t sel_ws_bytes;
@@ -449,11 +635,43 @@ inline int grid_x(long long items) {
     return (int)g;
 }
 
+// Levels 1..3 run in the fused register kernels when both extents are multiples of 8 and the pyramid has
+// at least 3 levels (and the 128-bit accesses are aligned); 0 selects the per-level kernels throughout
+// (odd extents, images below 64 pixels, MDIMG_HAAR_FUSED=0).
+int fused_levels(const Pyramid& p, int h, int w, const void* a, const void* b) {
+    static const bool off = [] { const char* e = getenv("MDIMG_HAAR_FUSED"); return e && e[0] == '0'; }();
+    if (off || p.L < 3 || (h & 7) || (w & 7)) return 0;
+    if ((((uintptr_t)a) | ((uintptr_t)b)) & 15) return 0;
+    return 3;
+}
+
 template <typename T, int MODE>
 void run_inverse(const Pyramid& p, const Dims& d, const int* skip, const WaveBufs& b,
-                 const float* coarse, const float* img_in, float* img_out, cudaStream_t st) {
+                 const float* coarse, const float* img_in, float* img_out, int K, cudaStream_t st) {
     T* r[2] = {reinterpret_cast<T*>(b.r0), reinterpret_cast<T*>(b.r1)};
     int cur = 0;
+    if (K > 0) {
+        for (int l = p.L; l > K; --l) {              // deeper levels: per-level kernels, never the last one
+            const int hd = p.H[l], wd = p.W[l];
+            dim3 grid(grid_x((long long)hd * wd), d.n_sel);
+            T* rout = r[cur];
+            if (l == p.L)
+                MDIMG_LAUNCH k_haar_inv<T, float, MODE, false><<<grid, NT, 0, st>>>(coarse, p.a_cap, wd, hd, wd, d, skip, l,
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, 2 * wd, img_in, img_out);
+            else
+                MDIMG_LAUNCH k_haar_inv<T, T, MODE, false><<<grid, NT, 0, st>>>(r[cur ^ 1], p.r_cap, 2 * p.W[l + 1], hd, wd, d, skip, l,
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, 2 * wd, img_in, img_out);
+            cur ^= 1;
+        }
+        dim3 grid(grid_x((long long)(d.h >> 3) * (d.w >> 3) * 2), d.n_sel);
+        if (K == p.L)
+            MDIMG_LAUNCH k_haar_inv_reg3<T, float, MODE><<<grid, NT, 0, st>>>(coarse, p.a_cap, p.W[K], d, skip, p, b.det, b.acc,
+                                                                                 img_in, img_out);
+        else
+            MDIMG_LAUNCH k_haar_inv_reg3<T, T, MODE><<<grid, NT, 0, st>>>(r[cur ^ 1], p.r_cap, 2 * p.W[K + 1], d, skip, p, b.det,
+                                                                             b.acc, img_in, img_out);
+        return;
+    }
     for (int l = p.L; l >= 1; --l) {
         const int hd = p.H[l], wd = p.W[l];
         dim3 grid(grid_x((long long)hd * wd), d.n_sel);
@@ -507,7 +725,12 @@ int wavelet_denoise_run(const float* in, float* out, const Dims& d, int mode_har
 
     // ---- forward ----
     float* abuf[2] = {b.a0, b.a1};
-    for (int l = 1; l <= p.L; ++l) {
+    const int K = fused_levels(p, d.h, d.w, in, out);
+    if (K > 0) {
+        dim3 grid(grid_x((long long)(d.h >> 3) * (d.w >> 3) * 2), d.n_sel);
+        MDIMG_LAUNCH k_haar_fwd_reg3<<<grid, NT, 0, stream>>>(in, d, skip, p, abuf[(K - 1) & 1], b.det, b.acc, b.l1, want_hist);
+    }
+    for (int l = K + 1; l <= p.L; ++l) {
         const int h0 = p.H[l - 1], w0 = p.W[l - 1];
         dim3 grid(grid_x((long long)p.H[l] * p.W[l]), d.n_sel);
         float* aout = abuf[(l - 1) & 1];
@@ -546,9 +769,9 @@ int wavelet_denoise_run(const float* in, float* out, const Dims& d, int mode_har
     MDIMG_LAUNCH k_wave_thresholds<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, p, b.acc, b.med, sigma_in, sigma_scale);
 
     // ---- inverse ----
-    if (mode_hard) run_inverse<float, 2>(p, d, skip, b, coarse, in, out, stream);
-    else if (sigma_in == nullptr) run_inverse<double, 0>(p, d, skip, b, coarse, in, out, stream);
-    else run_inverse<float, 1>(p, d, skip, b, coarse, in, out, stream);
+    if (mode_hard) run_inverse<float, 2>(p, d, skip, b, coarse, in, out, K, stream);
+    else if (sigma_in == nullptr) run_inverse<double, 0>(p, d, skip, b, coarse, in, out, K, stream);
+    else run_inverse<float, 1>(p, d, skip, b, coarse, in, out, K, stream);
     return check_launch("wavelet_denoise");
 }
 

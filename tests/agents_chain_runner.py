@@ -88,8 +88,10 @@ def chain(out_npz: str) -> dict:
         def emit(self, record):
             records.append((record.name, record.getMessage()))
 
-    logging.getLogger("pipeline.enhancement").addHandler(Keep())
-    logging.getLogger("mdimg_b200.enhancement").addHandler(Keep())
+    for name in ("pipeline.enhancement", "mdimg_b200.enhancement"):
+        lg = logging.getLogger(name)
+        lg.setLevel(logging.WARNING)            # the root logger of this helper only prints errors
+        lg.addHandler(Keep())
     use_reference = REFERENCE.exists()
     if use_reference:
         install_io_stubs()

@@ -386,3 +386,38 @@ def test_ingest_matches_load_dicom_pixel_path(ops, synth, dtype, slope, intercep
     ref = omet.ingest_frames(raw.astype(dtype), slope, intercept, mono1)
     np.testing.assert_array_equal(got, ref)
     assert got.min() == 0.0 and got.max() == 1.0
+
+
+def test_normalize_quotient_is_the_ieee_division_exhaustively(ops):
+    """mdimg_normalize_u16 divides through the slice's reciprocal plus one exact-residual correction; the
+    library checks that against the IEEE division for all 2.1e9 operand pairs 0 <= a <= denom <= 65535."""
+    import ctypes as C
+    count = C.c_ulonglong(123)
+    rc = ops.lib.mdimg_selftest_div16(C.byref(count), None)
+    assert rc == 0 and count.value == 0
+
+
+@pytest.mark.parametrize("shape", [(1024, 1024), (2048, 1088), (96, 160), (512, 768), (32, 32), (600, 200), (72, 1000)])
+@pytest.mark.parametrize("mode", ["soft", "hard", "light"])
+def test_wavelet_fused_levels(ops, synth, shape, mode):
+    """Extents divisible by 8 with L >= 3 take the fused register kernels for levels 1..3: L = 3 exactly
+    (96x160, 72x1000: the coarsest approximation feeds the fused inverse directly), L > 3 (per-level kernels
+    above level 3), odd level-3 band sizes (600x200: 75x25), L = 2 (32x32: per-level kernels only); three-slice
+    stacks (per-slice coefficient strides), one slice skipped in the light mode.  Same bits as the oracle."""
+    h, w = shape
+    rng = np.random.default_rng(h * 7 + w)
+    big = synth.unit_image(4100 + h, max(h, w))[:h, :w]
+    ims = [np.ascontiguousarray(big), np.ascontiguousarray(np.clip(big[::-1] * 0.5 + rng.normal(0, 0.02, (h, w)), 0, 1), dtype=np.float32)]
+    if mode == "light":
+        ims.append(np.full((h, w), 0.25, np.float32))            # sigma < 0.001: copied through untouched
+    x = torch.from_numpy(np.stack(ims)).to(ops.device)
+    out = torch.empty_like(x)
+    if mode == "light":
+        ops.light_denoise(x, out, 0.3)
+        refs = [oenh.light_denoise(im, 0.3) for im in ims]
+    else:
+        ops.wavelet_denoise(x, out, mode=mode)
+        refs = [ores.denoise_wavelet(im, mode=mode) for im in ims]
+    got = out.cpu().numpy()
+    for k, ref in enumerate(refs):
+        np.testing.assert_array_equal(got[k], ref)

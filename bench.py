@@ -386,7 +386,7 @@ def run_gpu(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device(f"cuda:{local}")
-    affinity = gpu_cpu_affinity(local) if (world > 1 and not args.no_affinity) else None
+    affinity = gpu_cpu_affinity(local) if (world > 1 and args.affinity) else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -630,7 +630,9 @@ def main() -> None:
     ap.add_argument("--e2e-schedule", default="", help="comma-separated chunk sizes of the end-to-end leg")
     ap.add_argument("--workers", type=int, default=4, help="host threads / CUDA streams driving chunks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-affinity", action="store_true", help="do not bind ranks to their GPU's local CPUs (N > 1)")
+    ap.add_argument("--affinity", action="store_true",
+                    help="bind each rank to the CPUs NVML reports as local to its GPU (N > 1; off by default: the pool's "
+                         "boxes are single-NUMA virtual machines where the set is the whole machine)")
     args = ap.parse_args()
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)

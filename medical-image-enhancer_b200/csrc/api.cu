@@ -355,12 +355,12 @@ int mdimg_light_denoise(const float* in, float* out, int n, int h, int w, const 
     if (!a.ok()) return set_error(MDIMG_ERR_WORKSPACE, "light_denoise: workspace too small (%zu > %zu)", a.off, ws_bytes);
     int rc = sigma_run(in, d, b.sigma, b.sws, b.sws_bytes, st);
     if (rc) return rc;
-    rc = skip_flags_run(d, b.sigma, 0.001, b.skip, st);
+    rc = skip_flags_run(d, b.sigma, 0.001, b.skip, st, skipped);
     if (rc) return rc;
-    rc = wavelet_denoise_run(in, b.tmp, d, 0, b.sigma, 0.5, b.skip, b.wws, b.wws_bytes, st);
-    if (rc) return rc;
-    // (1 - strength) * image + strength * denoised, python-float scalars acting as float32
-    return blend_skip_run(in, b.tmp, out, d, (float)(1.0 - strength), (float)strength, b.skip, skipped, st);
+    // (1 - strength) * image + strength * denoised, python-float scalars acting as float32: the blend is the
+    // epilogue of the last inverse wavelet level (skipped slices are copied through)
+    return wavelet_denoise_run(in, out, d, 0, b.sigma, 0.5, b.skip, b.wws, b.wws_bytes, st,
+                               (float)(1.0 - strength), (float)strength, 1);
 }
 
 int mdimg_bilateral(const float* in, float* out, int n, int h, int w, const int32_t* sel,

@@ -31,7 +31,8 @@ int clip01_run(const float* in, float* out, const Dims& d, cudaStream_t stream);
 // uint16(clip(rint(x * 65535), 0, 65535)) of the selected slices (16-bit export of an enhanced stack).
 int export_u16_run(const float* in, uint16_t* out, const Dims& d, cudaStream_t stream);
 // skip[s] = sigma[s] < thresh (device int[n]);  blend: out = skip ? a : c0*a + c1*b
-int skip_flags_run(const Dims& d, const double* sigma, double thresh, int* skip, cudaStream_t stream);
+int skip_flags_run(const Dims& d, const double* sigma, double thresh, int* skip, cudaStream_t stream,
+                   int* skipped_out = nullptr);
 int blend_skip_run(const float* a, const float* b, float* out, const Dims& d, float c0, float c1,
                    const int* skip, int* skipped_out, cudaStream_t stream);
 int copy_run(const float* in, float* out, const Dims& d, cudaStream_t stream);
@@ -58,9 +59,12 @@ size_t wavelet_workspace_bytes(int n, int n_sel, int h, int w);
 // mode_hard: 0 soft / 1 hard.  sigma_in: device [n] doubles or nullptr (estimate from the finest
 // Haar 'dd' band).  sigma_scale multiplies sigma_in (light denoise passes 0.5).
 // skip: device [n] int or nullptr; slices with skip[s] != 0 are copied through unchanged.
+// blend_on: the result is blend_c0 * in + blend_c1 * denoised (float32, numpy order) instead of the denoised
+// image -- _light_denoise's blend fused into the last inverse level; skipped slices are copied through.
 int wavelet_denoise_run(const float* in, float* out, const Dims& d, int mode_hard,
                         const double* sigma_in, double sigma_scale, const int* skip,
-                        void* ws, size_t ws_bytes, cudaStream_t stream);
+                        void* ws, size_t ws_bytes, cudaStream_t stream,
+                        float blend_c0 = 0.0f, float blend_c1 = 0.0f, int blend_on = 0);
 
 // ---- bilateral.cu --------------------------------------------------------------------------
 // spatial: host array of dd*dd doubles (row-major dy, dx), dd odd <= 9.

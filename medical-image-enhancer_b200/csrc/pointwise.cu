@@ -314,11 +314,14 @@ struct BlendSkipF {      // _light_denoise: (1-k)*x + k*den, or x itself where t
     }
 };
 
-__global__ void k_skip_flags(Dims d, const double* __restrict__ sigma, double thresh, int* __restrict__ skip) {
+__global__ void k_skip_flags(Dims d, const double* __restrict__ sigma, double thresh, int* __restrict__ skip,
+                             int* __restrict__ skipped_out) {
     int si = blockIdx.x * blockDim.x + threadIdx.x;
     if (si >= d.n_sel) return;
     int s = slice_of(d.sel, si);
-    skip[s] = sigma[s] < thresh ? 1 : 0;      // NaN compares false, as in the reference
+    const int v = sigma[s] < thresh ? 1 : 0;  // NaN compares false, as in the reference
+    skip[s] = v;
+    if (skipped_out) skipped_out[s] = v;
 }
 
 struct ClipF {
@@ -412,9 +415,10 @@ int blend_skip_run(const float* a, const float* b, float* out, const Dims& d, fl
     return check_launch("blend_skip");
 }
 
-int skip_flags_run(const Dims& d, const double* sigma, double thresh, int* skip, cudaStream_t stream) {
+int skip_flags_run(const Dims& d, const double* sigma, double thresh, int* skip, cudaStream_t stream,
+                   int* skipped_out) {
     if (d.n_sel == 0) return MDIMG_OK;
-    MDIMG_LAUNCH k_skip_flags<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, sigma, thresh, skip);
+    MDIMG_LAUNCH k_skip_flags<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, sigma, thresh, skip, skipped_out);
     return check_launch("skip_flags");
 }
 

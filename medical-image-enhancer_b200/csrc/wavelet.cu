@@ -417,6 +417,14 @@ __global__ void k_wave_thresholds(Dims d, Pyramid p, WaveAcc* __restrict__ acc,
     }
 }
 
+// Optional epilogue of the last inverse level: out = c0 * x + c1 * denoised in float32 (products and sum
+// rounded separately, numpy's order) -- the blend of _light_denoise (pipeline/enhancement.py:93) fused into
+// the store, so the denoised image never makes a round trip through HBM.
+struct Blend { float c0, c1; int on; };
+__device__ __forceinline__ float blend_px(const Blend& bl, float x, float v) {
+    return bl.on ? __fadd_rn(__fmul_rn(bl.c0, x), __fmul_rn(bl.c1, v)) : v;
+}
+
 template <typename T> struct Ops;
 template <> struct Ops<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
@@ -455,7 +463,7 @@ k_haar_inv(const TA* __restrict__ ain, long long a_stride, int a_pitch, int hd, 
            const int* __restrict__ skip, int level, const float* __restrict__ det,
            long long det_stride, long long det_off, const WaveAcc* __restrict__ acc,
            T* __restrict__ rout, long long r_stride, int out_pitch,
-           const float* __restrict__ img_in, float* __restrict__ img_out) {
+           const float* __restrict__ img_in, float* __restrict__ img_out, Blend bl) {
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
     if (skip && skip[s]) {
@@ -493,11 +501,13 @@ k_haar_inv(const TA* __restrict__ ain, long long a_stride, int a_pitch, int hd, 
         const T o11 = O::add(O::mul(S, a_o), O::mul(NS, d_o));
         if (LAST) {
             float* o = img_out + (size_t)s * d.h * d.w;
+            const float* xi = img_in + (size_t)s * d.h * d.w;      // read only when blending (same pixel this thread writes)
             const int Y = 2 * y, X = 2 * x;
-            if (Y < d.h && X < d.w) o[(size_t)Y * d.w + X] = (float)o00;
-            if (Y < d.h && X + 1 < d.w) o[(size_t)Y * d.w + X + 1] = (float)o01;
-            if (Y + 1 < d.h && X < d.w) o[(size_t)(Y + 1) * d.w + X] = (float)o10;
-            if (Y + 1 < d.h && X + 1 < d.w) o[(size_t)(Y + 1) * d.w + X + 1] = (float)o11;
+            auto put = [&](size_t at, T v) { o[at] = blend_px(bl, bl.on ? xi[at] : 0.0f, (float)v); };
+            if (Y < d.h && X < d.w) put((size_t)Y * d.w + X, o00);
+            if (Y < d.h && X + 1 < d.w) put((size_t)Y * d.w + X + 1, o01);
+            if (Y + 1 < d.h && X < d.w) put((size_t)(Y + 1) * d.w + X, o10);
+            if (Y + 1 < d.h && X + 1 < d.w) put((size_t)(Y + 1) * d.w + X + 1, o11);
         } else {
             T* o = rout + (size_t)si * r_stride;
             const size_t b0 = (size_t)(2 * y) * out_pitch + 2 * x;
@@ -533,11 +543,12 @@ template <typename T, typename TA, int MODE>
 __global__ void __launch_bounds__(NT)
 k_haar_inv_reg3(const TA* __restrict__ ain, long long a_stride, int a_pitch, Dims d, const int* __restrict__ skip,
                 Pyramid p, const float* __restrict__ det, const WaveAcc* __restrict__ acc,
-                const float* __restrict__ img_in, float* __restrict__ img_out) {
+                const float* __restrict__ img_in, float* __restrict__ img_out, Blend bl) {
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
     const int tid = threadIdx.x;
     float* dst = img_out + (size_t)s * d.h * d.w;
+    const float* xin = img_in + (size_t)s * d.h * d.w;
     if (skip && skip[s]) {                          // untouched slice: copy through
         const float* a = img_in + (size_t)s * d.h * d.w;
         const long long len = d.px();
@@ -588,10 +599,23 @@ k_haar_inv_reg3(const TA* __restrict__ ain, long long a_stride, int a_pitch, Dim
             const Quad<T> q3r = haar_inv_2x2<T>(a1[yy][3], shrink<T, MODE>(ad.w, t1a), shrink<T, MODE>(da.w, t1b), shrink<T, MODE>(dd.w, t1c));
             float4* r0 = reinterpret_cast<float4*>(blk + (size_t)(2 * yy) * d.w);
             float4* r1 = reinterpret_cast<float4*>(blk + (size_t)(2 * yy + 1) * d.w);
-            r0[0] = make_float4((float)q0.o00, (float)q0.o01, (float)q1.o00, (float)q1.o01);
-            r0[1] = make_float4((float)q2.o00, (float)q2.o01, (float)q3r.o00, (float)q3r.o01);
-            r1[0] = make_float4((float)q0.o10, (float)q0.o11, (float)q1.o10, (float)q1.o11);
-            r1[1] = make_float4((float)q2.o10, (float)q2.o11, (float)q3r.o10, (float)q3r.o11);
+            float4 e0 = make_float4((float)q0.o00, (float)q0.o01, (float)q1.o00, (float)q1.o01);
+            float4 e1 = make_float4((float)q2.o00, (float)q2.o01, (float)q3r.o00, (float)q3r.o01);
+            float4 f0 = make_float4((float)q0.o10, (float)q0.o11, (float)q1.o10, (float)q1.o11);
+            float4 f1 = make_float4((float)q2.o10, (float)q2.o11, (float)q3r.o10, (float)q3r.o11);
+            if (bl.on) {                            // the same 16 pixels of the input image, read before they are written
+                const float* xb = xin + (size_t)(8 * by) * d.w + 8 * bx;
+                const float4* x0 = reinterpret_cast<const float4*>(xb + (size_t)(2 * yy) * d.w);
+                const float4* x1 = reinterpret_cast<const float4*>(xb + (size_t)(2 * yy + 1) * d.w);
+                auto mix = [&](float4& v, const float4 x) {
+                    v.x = blend_px(bl, x.x, v.x); v.y = blend_px(bl, x.y, v.y);
+                    v.z = blend_px(bl, x.z, v.z); v.w = blend_px(bl, x.w, v.w);
+                };
+                const float4 xa = x0[0], xb4 = x0[1], xc = x1[0], xd = x1[1];
+                mix(e0, xa); mix(e1, xb4); mix(f0, xc); mix(f1, xd);
+            }
+            r0[0] = e0; r0[1] = e1;
+            r1[0] = f0; r1[1] = f1;
         }
     }
 }
@@ -647,7 +671,7 @@ int fused_levels(const Pyramid& p, int h, int w, const void* a, const void* b) {
 
 template <typename T, int MODE>
 void run_inverse(const Pyramid& p, const Dims& d, const int* skip, const WaveBufs& b,
-                 const float* coarse, const float* img_in, float* img_out, int K, cudaStream_t st) {
+                 const float* coarse, const float* img_in, float* img_out, int K, Blend bl, cudaStream_t st) {
     T* r[2] = {reinterpret_cast<T*>(b.r0), reinterpret_cast<T*>(b.r1)};
     int cur = 0;
     if (K > 0) {
@@ -657,19 +681,19 @@ void run_inverse(const Pyramid& p, const Dims& d, const int* skip, const WaveBuf
             T* rout = r[cur];
             if (l == p.L)
                 MDIMG_LAUNCH k_haar_inv<T, float, MODE, false><<<grid, NT, 0, st>>>(coarse, p.a_cap, wd, hd, wd, d, skip, l,
-                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, 2 * wd, img_in, img_out);
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, 2 * wd, img_in, img_out, bl);
             else
                 MDIMG_LAUNCH k_haar_inv<T, T, MODE, false><<<grid, NT, 0, st>>>(r[cur ^ 1], p.r_cap, 2 * p.W[l + 1], hd, wd, d, skip, l,
-                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, 2 * wd, img_in, img_out);
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, 2 * wd, img_in, img_out, bl);
             cur ^= 1;
         }
         dim3 grid(grid_x((long long)(d.h >> 3) * (d.w >> 3) * 2), d.n_sel);
         if (K == p.L)
             MDIMG_LAUNCH k_haar_inv_reg3<T, float, MODE><<<grid, NT, 0, st>>>(coarse, p.a_cap, p.W[K], d, skip, p, b.det, b.acc,
-                                                                                 img_in, img_out);
+                                                                                 img_in, img_out, bl);
         else
             MDIMG_LAUNCH k_haar_inv_reg3<T, T, MODE><<<grid, NT, 0, st>>>(r[cur ^ 1], p.r_cap, 2 * p.W[K + 1], d, skip, p, b.det,
-                                                                             b.acc, img_in, img_out);
+                                                                             b.acc, img_in, img_out, bl);
         return;
     }
     for (int l = p.L; l >= 1; --l) {
@@ -682,19 +706,19 @@ void run_inverse(const Pyramid& p, const Dims& d, const int* skip, const WaveBuf
         if (first) {
             if (last)
                 MDIMG_LAUNCH k_haar_inv<T, float, MODE, true><<<grid, NT, 0, st>>>(coarse, p.a_cap, wd, hd, wd, d, skip, l,
-                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out);
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out, bl);
             else
                 MDIMG_LAUNCH k_haar_inv<T, float, MODE, false><<<grid, NT, 0, st>>>(coarse, p.a_cap, wd, hd, wd, d, skip, l,
-                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out);
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out, bl);
         } else {
             const T* ain = r[cur ^ 1];
             const int a_pitch = 2 * p.W[l + 1];
             if (last)
                 MDIMG_LAUNCH k_haar_inv<T, T, MODE, true><<<grid, NT, 0, st>>>(ain, p.r_cap, a_pitch, hd, wd, d, skip, l,
-                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out);
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out, bl);
             else
                 MDIMG_LAUNCH k_haar_inv<T, T, MODE, false><<<grid, NT, 0, st>>>(ain, p.r_cap, a_pitch, hd, wd, d, skip, l,
-                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out);
+                    b.det, p.det_per_slice, p.off[l], b.acc, rout, p.r_cap, out_pitch, img_in, img_out, bl);
         }
         cur ^= 1;
     }
@@ -712,7 +736,8 @@ size_t wavelet_workspace_bytes(int n, int n_sel, int h, int w) {
 
 int wavelet_denoise_run(const float* in, float* out, const Dims& d, int mode_hard,
                         const double* sigma_in, double sigma_scale, const int* skip,
-                        void* ws, size_t ws_bytes, cudaStream_t stream) {
+                        void* ws, size_t ws_bytes, cudaStream_t stream, float blend_c0, float blend_c1, int blend_on) {
+    const Blend bl = {blend_c0, blend_c1, blend_on};
     if (d.n_sel == 0) return MDIMG_OK;
     Pyramid p = make_pyramid(d.h, d.w);
     Arena a(ws, ws_bytes);
@@ -769,9 +794,9 @@ int wavelet_denoise_run(const float* in, float* out, const Dims& d, int mode_har
     MDIMG_LAUNCH k_wave_thresholds<<<(d.n_sel + 127) / 128, 128, 0, stream>>>(d, p, b.acc, b.med, sigma_in, sigma_scale);
 
     // ---- inverse ----
-    if (mode_hard) run_inverse<float, 2>(p, d, skip, b, coarse, in, out, K, stream);
-    else if (sigma_in == nullptr) run_inverse<double, 0>(p, d, skip, b, coarse, in, out, K, stream);
-    else run_inverse<float, 1>(p, d, skip, b, coarse, in, out, K, stream);
+    if (mode_hard) run_inverse<float, 2>(p, d, skip, b, coarse, in, out, K, bl, stream);
+    else if (sigma_in == nullptr) run_inverse<double, 0>(p, d, skip, b, coarse, in, out, K, bl, stream);
+    else run_inverse<float, 1>(p, d, skip, b, coarse, in, out, K, bl, stream);
     return check_launch("wavelet_denoise");
 }
 

@@ -1092,9 +1092,45 @@ size_t metrics_workspace_bytes(int n_sel, int h, int w) {
     return a.off;
 }
 
+static int metrics_run_batch(const float* img, const Dims& d, const PctPlan& plan, int flags, double* out,
+                             void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// Slices per sub-batch of one mdimg_metrics call.  The passes after the strip kernel re-read x, |grad| and
+// |dd| (level-1 scan, <= 3 refinement passes, the |grad| statistics): run over a whole 512-slice chunk they
+// stream those arrays from HBM every time (35 B/px of DRAM traffic measured); run sub-batch by sub-batch,
+// with every kernel of a sub-batch issued before the next sub-batch starts, the re-reads hit the 126 MB L2.
+// MDIMG_METRICS_SUB=<slices> overrides (0 = one batch).
+static int metrics_sub_slices(int h, int w) {
+    static const int env = [] { const char* e = getenv("MDIMG_METRICS_SUB"); return e ? atoi(e) : -1; }();
+    if (env >= 0) return env;
+    return 0;
+}
+
 int metrics_run(const float* img, const Dims& d, const PctPlan& plan, int flags, double* out,
                 void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (d.n_sel == 0) return MDIMG_OK;
+    const int sub = metrics_sub_slices(d.h, d.w);
+    if (sub <= 0 || d.n_sel <= sub) return metrics_run_batch(img, d, plan, flags, out, ws, ws_bytes, stream);
+    for (int a0 = 0; a0 < d.n_sel; a0 += sub) {
+        const int cnt = d.n_sel - a0 < sub ? d.n_sel - a0 : sub;
+        Dims ds = d;
+        int rc;
+        if (d.sel) {                   // positions a0 .. a0+cnt of the selection; arrays stay indexed by slice id
+            ds.sel = d.sel + a0;
+            ds.n_sel = cnt;
+            rc = metrics_run_batch(img, ds, plan, flags, out, ws, ws_bytes, stream);
+        } else {                       // contiguous slices: shift the bases
+            ds.n = cnt;
+            ds.n_sel = cnt;
+            rc = metrics_run_batch(img + (size_t)a0 * d.h * d.w, ds, plan, flags, out + (size_t)a0 * MC_COLS, ws, ws_bytes, stream);
+        }
+        if (rc) return rc;
+    }
+    return MDIMG_OK;
+}
+
+static int metrics_run_batch(const float* img, const Dims& d, const PctPlan& plan, int flags, double* out,
+                             void* ws, size_t ws_bytes, cudaStream_t stream) {
     Arena a(ws, ws_bytes);
     MetBufs m;
     carve_metrics(a, d.n, d.n_sel, d.h, d.w, m);

@@ -275,6 +275,7 @@ constexpr int NV16 = SWP;             // axis-0 tasks of the 16-window: every in
 constexpr int NV7 = SW + 6;           // axis-0 tasks of the 7-window: input columns 5 .. SW+10 (threads 160..293)
 constexpr int SEG = 8;                // axis-1: outputs per (row, segment) task
 constexpr int NACC = 11;
+constexpr int STAGE_P = 144;            // floats per staged row (SWP rounded up to a 16-byte multiple)
 
 struct Smem {
     double Xs[RING * P];              // x
@@ -284,7 +285,31 @@ struct Smem {
     unsigned hx[SEL_L1_BINS];
     unsigned hg[SEL_L1_BINS];
     double red[NACC * 32];
+    float stage[SR * STAGE_P];        // bulk-copy landing zone: the 8 float32 rows of the load block in flight
+    unsigned long long mbar;          // mbarrier the bulk copies complete on
 };
+
+// ---- bulk asynchronous copies (TMA engine, cp.async.bulk) of whole row segments into shared memory ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned a = smem_u32(bar);
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    }
+}
 
 // v rounded to float32 precision, as a double.  FAST: v is 0 or a normal float32-range magnitude
 // (guaranteed by the caller); the sum lands in the binade whose double spacing is the float32
@@ -382,7 +407,7 @@ __device__ __forceinline__ void horizontal(const double* vS, const double* vQ, i
 
 template <bool FULL>
 __global__ void __launch_bounds__(NT, 2)
-k_strip_stats(const float* __restrict__ img, Dims d, int band_h, int want16, MetAcc* __restrict__ acc,
+k_strip_stats(const float* __restrict__ img, Dims d, int band_h, int want16, int bulk, MetAcc* __restrict__ acc,
               float* __restrict__ gout, unsigned* __restrict__ l1x, unsigned* __restrict__ l1g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -401,37 +426,66 @@ k_strip_stats(const float* __restrict__ img, Dims d, int band_h, int want16, Met
         for (int i = tid; i < 256; i += NT) sm.h256[i] = 0;
         for (int i = tid; i < SEL_L1_BINS; i += NT) { sm.hx[i] = 0; sm.hg[i] = 0; }
     }
-    if (tid == 0) slow_s = 0;
+    if (tid == 0) {
+        slow_s = 0;
+        if (bulk) mbar_init(&sm.mbar, SR);        // one arrival (+ its bytes) per loader warp and load block
+    }
     __syncthreads();
 
     // ---- loader: warp w < 8 owns row w of a load block, a lane its columns lane + 32 k ----
+    // bulk path (row pitch and bases 16-byte aligned): lane 0 of the warp hands the row's in-image column
+    // range [cb, ce) to the TMA engine as ONE cp.async.bulk into the staging row; only the <= 8 reflected
+    // border columns of the first / last strip are fetched with ordinary loads.  The copy of load block
+    // B + 3 is in flight during the whole step B; stash() waits for it on the mbarrier.
+    const int cb = x0 == 0 ? HL : 0;                                   // first staged input column
+    const int ce = min(STAGE_P, d.w - (x0 - HL));                      // end of the staged range (multiple of 4)
+    unsigned phase = 0;
     constexpr int NC = (SWP + 31) / 32;           // 5
     int gx[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) gx[k] = refl_sym_fast(x0 - HL + lane + 32 * k, d.w);
     float pf[NC];
     bool bad = false;
-    auto fetch = [&](int lb) {                    // load block lb -> registers
+    auto fetch = [&](int lb) {                    // load block lb -> staging row (bulk) / registers
         if (wid < SR) {
             const float* row = src + (size_t)refl_sym_fast(yb0 - HL + lb * SR + wid, d.h) * d.w;
+            if (bulk) {
+                if (lane == 0) {
+                    const unsigned bytes = (unsigned)(ce - cb) * 4u;
+                    mbar_expect_tx(&sm.mbar, bytes);
+                    bulk_g2s(sm.stage + wid * STAGE_P + cb, row + (x0 - HL + cb), bytes, &sm.mbar);
+                }
 #pragma unroll
-            for (int k = 0; k < NC; ++k)
-                if (lane + 32 * k < SWP) pf[k] = row[gx[k]];
+                for (int k = 0; k < NC; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c < SWP && (c < cb || c >= ce)) pf[k] = row[gx[k]];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NC; ++k)
+                    if (lane + 32 * k < SWP) pf[k] = row[gx[k]];
+            }
         }
     };
-    auto stash = [&](int off) {                   // registers -> the ring block at offset `off`, as doubles
+    auto stash = [&](int off) {                   // staging row / registers -> the ring block at offset `off`, as doubles
         if (wid < SR) {
+            if (bulk) {
+                mbar_wait(&sm.mbar, phase);
+                phase ^= 1u;
+            }
             const int r = off + wid * P + lane;
 #pragma unroll
             for (int k = 0; k < NC; ++k)
                 if (lane + 32 * k < SWP) {
-                    const float v = pf[k];
+                    const int c = lane + 32 * k;
+                    const float v = (bulk && c >= cb && c < ce) ? sm.stage[wid * STAGE_P + c] : pf[k];
                     // the FP64-pipe rounding needs 0 or a normal magnitude whose square is normal too
                     const unsigned u = __float_as_uint(v);
                     bad |= (u != 0u) && (u - 0x21800000u >= 0x3c000000u);      // outside [2^-60, 2^60) or negative
                     sm.Xs[r + 32 * k] = (double)v;
                     sm.Xq[r + 32 * k] = (double)__fmul_rn(v, v);
                 }
+            __syncwarp();                         // the staging row is free again: this warp's next copy may land
         }
     };
 
@@ -601,8 +655,14 @@ void launch(const float* img, const Dims& d, int want16, MetAcc* acc, float* gou
     opt_in_shared_memory(k_strip_stats<FULL>, sizeof(Smem), devices_done);
     const int bh = band_rows(d.n_sel, d.h, d.w);
     const int strips = (d.w + SW - 1) / SW, bands = (d.h + bh - 1) / bh;
+    // Bulk (TMA engine) row copies need 16-byte aligned row segments: row pitch a multiple of 4 pixels, aligned
+    // base.  Measured on B200 (512 slices): mdimg_quality 1.25 ms with them against 1.09 ms with the register
+    // prefetch, mdimg_metrics 3.69 against 3.55 -- a 576-byte copy per row is too small a unit for the engine and
+    // the staging row adds a shared-memory round trip -- so the path is opt-in (MDIMG_STRIP_BULK=1).
+    static const bool bulk_on = [] { const char* e = getenv("MDIMG_STRIP_BULK"); return e && e[0] == '1'; }();
+    const int bulk = (bulk_on && (d.w & 3) == 0 && (((uintptr_t)img) & 15) == 0 && d.w >= 16) ? 1 : 0;
     MDIMG_LAUNCH k_strip_stats<FULL><<<dim3(strips * bands, d.n_sel), NT, sizeof(Smem), stream>>>(
-        img, d, bh, want16, acc, gout, l1x, l1g);
+        img, d, bh, want16, bulk, acc, gout, l1x, l1g);
 }
 
 }  // namespace strip

@@ -421,3 +421,42 @@ def test_wavelet_fused_levels(ops, synth, shape, mode):
     got = out.cpu().numpy()
     for k, ref in enumerate(refs):
         np.testing.assert_array_equal(got[k], ref)
+
+
+_VARIANT_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from mdimg_b200.stack import get_ops
+ops = get_ops()
+rng = np.random.default_rng(11)
+out = {}
+for k, shape in enumerate([(3, 128, 256), (2, 96, 520), (1, 64, 136), (2, 40, 12), (1, 300, 1000)]):
+    x = torch.from_numpy(rng.random(shape, dtype=np.float32)).to(ops.device)
+    out[f"m{k}"] = ops.metrics(x, with_niqe=True).cpu().numpy()
+    out[f"q{k}"] = ops.quality(x, niqe=True).cpu().numpy()
+np.savez(sys.argv[2], **out)
+"""
+
+
+@pytest.mark.parametrize("env", [{"MDIMG_STRIP_BULK": "1"}, {"MDIMG_METRICS_TILES": "1"}, {"MDIMG_METRICS_SUB": "1"}])
+def test_metrics_kernel_variants_give_identical_rows(tmp_path, env):
+    """The optional paths of the metrics kernels -- cp.async.bulk (TMA engine) row loader of the strip kernel,
+    the round-1 tile kernels, sub-batched calls -- are selected per process by environment variables: each must
+    reproduce the default path's result rows (first, last and interior strips; widths that are / are not a multiple
+    of the strip; a 12-pixel-wide image)."""
+    import os
+    import subprocess
+    import sys
+    root = str(__import__("pathlib").Path(__file__).resolve().parent.parent)
+    outs = []
+    for k, e in enumerate(({}, env)):
+        path = tmp_path / f"rows{k}.npz"
+        subprocess.run([sys.executable, "-c", _VARIANT_CHILD, root, str(path)], check=True, timeout=300,
+                       env={**{kk: v for kk, v in os.environ.items() if not kk.startswith("MDIMG_")}, **e})
+        outs.append(np.load(path))
+    for key in outs[0].files:
+        a, b = outs[0][key], outs[1][key]
+        if "MDIMG_METRICS_TILES" in env:      # other summation order of the float64 accumulators
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-12, err_msg=key)
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-12, atol=0, err_msg=key)

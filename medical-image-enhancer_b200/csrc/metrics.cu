@@ -1143,7 +1143,11 @@ void sigma_produce(const float* img, const Dims& d, MetAcc* acc, SigmaBufs& b, c
     cudaMemsetAsync(b.l1, 0, (size_t)d.n_sel * SEL_L1_BINS * sizeof(unsigned), stream);
     const int tasks = ((wd + DB_COLS - 1) / DB_COLS) * ((hd + DB_ROWS - 1) / DB_ROWS);     // warp tasks per slice
     int gx = (tasks + NT / 32 - 1) / (NT / 32);
-    const int cap = d.n_sel >= 64 ? 4 : 64;       // few long-lived blocks per slice when the batch fills the machine: one histogram flush each
+    // few long-lived blocks per slice (one histogram flush each) once the batch alone fills the machine: about two
+    // waves of five resident blocks on 148 SMs in total, never fewer than four per slice
+    int cap = (1480 + d.n_sel - 1) / d.n_sel;
+    if (cap < 4) cap = 4;
+    if (cap > 64) cap = 64;
     if (gx > cap) gx = cap;
     dim3 grid(gx, d.n_sel);
     MDIMG_LAUNCH k_db2_dd<<<grid, NT, 0, stream>>>(img, d, hd, wd, b.absdd, b.l1, acc);

@@ -162,6 +162,7 @@ struct RefineCtx {
     const unsigned* ulo; const unsigned* uspan; const int* ushift;
     unsigned* hbase;
     int lane;
+    unsigned lo0, span0;                           // the slice's only unresolved range (ONE variants)
 };
 
 __device__ __forceinline__ void refine_account(const RefineCtx& c, unsigned key, unsigned mask) {
@@ -189,20 +190,30 @@ __device__ __forceinline__ void refine_drain32(RefineCtx& c) {
 }
 
 // All 32 lanes call (valid = this lane holds an element).
-template <bool ABS>
+// ONE: the slice has a single unresolved key range (always so for |grad| and |dd|, whose queries are one percentile):
+// the element is tested against that range directly -- key, subtract, compare: 4 instructions instead of the 12 of the
+// level-1 bin + flag lookup, and exact, so later passes queue nothing but the elements they must count.
+template <bool ABS, bool ONE>
 __device__ __forceinline__ void refine_visit(RefineCtx& c, float f, bool valid) {
-    f = __fadd_rn(ABS ? fabsf(f) : f, 0.0f);
-    unsigned hit;      // shared-window address kept in a register: ptxas otherwise rebuilds it per element
-    asm("ld.shared.u8 %0, [%1];" : "=r"(hit) : "r"(c.flag_sa + (unsigned)sel_bin1(f)));
+    unsigned hit, key;
+    if (ONE) {
+        key = ABS ? (__float_as_uint(f) | 0x80000000u) : f2key(__fadd_rn(f, 0.0f));   // |f| >= 0: its key is bits | sign bit
+        hit = (key - c.lo0) <= c.span0;
+    } else {
+        f = __fadd_rn(ABS ? fabsf(f) : f, 0.0f);
+        // shared-window address kept in a register: ptxas otherwise rebuilds it per element
+        asm("ld.shared.u8 %0, [%1];" : "=r"(hit) : "r"(c.flag_sa + (unsigned)sel_bin1(f)));
+        key = f2key(f);
+    }
     const unsigned m = __ballot_sync(0xffffffffu, valid && hit);
     if (m) {                                       // warp-uniform
-        if (valid && hit) c.q[c.qn + __popc(m & ((1u << c.lane) - 1u))] = f2key(f);
+        if (valid && hit) c.q[c.qn + __popc(m & ((1u << c.lane) - 1u))] = key;
         c.qn += __popc(m);
         if (c.qn >= 32) refine_drain32(c);
     }
 }
 
-template <bool ABS>
+template <bool ABS, bool ONE>
 __device__ __forceinline__ void refine_stream(RefineCtx& c, const float* __restrict__ v, int len, int tid, int nthr) {
     const int lane = c.lane;
     // head: the 0..3 elements in front of the first 16-byte boundary (slices of odd length -- the 257 x 257
@@ -211,7 +222,7 @@ __device__ __forceinline__ void refine_stream(RefineCtx& c, const float* __restr
     if (head > len) head = len;
     if (tid - lane < head) {                       // first warp of the slice only (warp-uniform)
         const bool ok = tid < head;
-        refine_visit<ABS>(c, ok ? v[tid] : 0.0f, ok);
+        refine_visit<ABS, ONE>(c, ok ? v[tid] : 0.0f, ok);
     }
     const float* va = v + head;
     const int rem = len - head;
@@ -221,19 +232,19 @@ __device__ __forceinline__ void refine_stream(RefineCtx& c, const float* __restr
     // four independent 128-bit loads in flight while the whole warp is in range (warp-uniform test)
     for (; i - lane + 31 + 3 * nthr < n4; i += 4 * nthr) {
         const float4 a = v4[i], b = v4[i + nthr], d = v4[i + 2 * nthr], e = v4[i + 3 * nthr];
-        refine_visit<ABS>(c, a.x, true); refine_visit<ABS>(c, a.y, true); refine_visit<ABS>(c, a.z, true); refine_visit<ABS>(c, a.w, true);
-        refine_visit<ABS>(c, b.x, true); refine_visit<ABS>(c, b.y, true); refine_visit<ABS>(c, b.z, true); refine_visit<ABS>(c, b.w, true);
-        refine_visit<ABS>(c, d.x, true); refine_visit<ABS>(c, d.y, true); refine_visit<ABS>(c, d.z, true); refine_visit<ABS>(c, d.w, true);
-        refine_visit<ABS>(c, e.x, true); refine_visit<ABS>(c, e.y, true); refine_visit<ABS>(c, e.z, true); refine_visit<ABS>(c, e.w, true);
+        refine_visit<ABS, ONE>(c, a.x, true); refine_visit<ABS, ONE>(c, a.y, true); refine_visit<ABS, ONE>(c, a.z, true); refine_visit<ABS, ONE>(c, a.w, true);
+        refine_visit<ABS, ONE>(c, b.x, true); refine_visit<ABS, ONE>(c, b.y, true); refine_visit<ABS, ONE>(c, b.z, true); refine_visit<ABS, ONE>(c, b.w, true);
+        refine_visit<ABS, ONE>(c, d.x, true); refine_visit<ABS, ONE>(c, d.y, true); refine_visit<ABS, ONE>(c, d.z, true); refine_visit<ABS, ONE>(c, d.w, true);
+        refine_visit<ABS, ONE>(c, e.x, true); refine_visit<ABS, ONE>(c, e.y, true); refine_visit<ABS, ONE>(c, e.z, true); refine_visit<ABS, ONE>(c, e.w, true);
     }
     for (; i - lane < n4; i += nthr) {
         const bool ok = i < n4;
         const float4 q = ok ? v4[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        refine_visit<ABS>(c, q.x, ok); refine_visit<ABS>(c, q.y, ok); refine_visit<ABS>(c, q.z, ok); refine_visit<ABS>(c, q.w, ok);
+        refine_visit<ABS, ONE>(c, q.x, ok); refine_visit<ABS, ONE>(c, q.y, ok); refine_visit<ABS, ONE>(c, q.z, ok); refine_visit<ABS, ONE>(c, q.w, ok);
     }
     for (int k = (n4 << 2) + tid; k - lane < rem; k += nthr) {
         const bool ok = k < rem;
-        refine_visit<ABS>(c, ok ? va[k] : 0.0f, ok);
+        refine_visit<ABS, ONE>(c, ok ? va[k] : 0.0f, ok);
     }
     __syncwarp();
     if (lane < c.qn) refine_account(c, c.q[lane], 0u);            // leftovers
@@ -279,8 +290,15 @@ k_sel_refine(Params P, Dims d) {
     c.q = queue[threadIdx.x >> 5];
     c.qn = 0;
     c.nu = nu; c.ulo = ulo; c.uspan = uspan; c.ushift = ushift; c.hbase = hbase; c.lane = lane;
-    if (J.opts & SEL_ABS) refine_stream<true>(c, v, J.len, tid, nthr);
-    else refine_stream<false>(c, v, J.len, tid, nthr);
+    c.lo0 = ulo[0]; c.span0 = uspan[0];
+    const bool one = nu == 1;                      // block-uniform
+    if (J.opts & SEL_ABS) {
+        if (one) refine_stream<true, true>(c, v, J.len, tid, nthr);
+        else refine_stream<true, false>(c, v, J.len, tid, nthr);
+    } else {
+        if (one) refine_stream<false, true>(c, v, J.len, tid, nthr);
+        else refine_stream<false, false>(c, v, J.len, tid, nthr);
+    }
 
     // ---- last block of this slice: scan the digit histograms, narrow the ranges ----
     __threadfence();

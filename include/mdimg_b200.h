@@ -184,7 +184,8 @@ int mdimg_light_denoise(const float* in, float* out, int n, int h, int w, const 
 int mdimg_bilateral(const float* in, float* out, int n, int h, int w, const int32_t* sel,
                     int n_sel, int d, const double* spatial, double sigma_color, void* stream);
 /* denoise_tv_chambolle(image, weight, channel_axis=None) (pipeline/enhancement.py:311,349).
- * iters: device int32[n] or NULL.  Synchronises `stream` every few iterations. */
+ * iters: device int32[n] or NULL.  The call never drains `stream`: the launch sequence is cut short from live-slice
+ * counts the kernels report through host-mapped memory, the host waits only on events a few launches back. */
 int mdimg_tv_chambolle(const float* in, float* out, int n, int h, int w, const int32_t* sel,
                        int n_sel, double weight, double eps, int max_iter, int32_t* iters,
                        void* ws, size_t ws_bytes, void* stream);

@@ -329,24 +329,25 @@ int mdimg_enhance(const float* in, float* out, int n, int h, int w, const mdimg_
         }
     rc = mdimg_clip01(cur, cur, n, h, w, nullptr, 0, stream);
     if (rc) return rc;
-    std::vector<int32_t> err(n, 0);
-    rc = flush_checks(c, main_pass, err);
-    if (rc) return rc;
-    std::vector<int32_t> tv_iters(n, 0);
-    const bool tv_main = main_pass.tv_ran;
-    if (tv_main) { rc = c.fetch(tv_iters.data(), c.b.iters, sizeof(int32_t) * n); if (rc) return rc; }
-
     // ---- safeguards: one metrics pass yields what all three look at; only modified slices are re-measured ----
+    // The metrics passes are enqueued BEFORE the first host read-back: the GPU works on them while the host waits for
+    // the step flags, and the later read-backs find their data already there.
     const double* rows_b = rows_before_in;
     if (!rows_b) {
         rc = metrics(in, c.b.rows_before, nullptr, 0);
         if (rc) return rc;
         rows_b = c.b.rows_before;
     }
+    rc = metrics(cur, rows, nullptr, 0);
+    if (rc) return rc;
+    std::vector<int32_t> err(n, 0);
+    rc = flush_checks(c, main_pass, err);
+    if (rc) return rc;
+    std::vector<int32_t> tv_iters(n, 0);
+    const bool tv_main = main_pass.tv_ran;
+    if (tv_main) { rc = c.fetch(tv_iters.data(), c.b.iters, sizeof(int32_t) * n); if (rc) return rc; }
     std::vector<double> hb((size_t)n * MC_COLS), hr((size_t)n * MC_COLS);
     rc = c.fetch(hb.data(), rows_b, sizeof(double) * hb.size());
-    if (rc) return rc;
-    rc = metrics(cur, rows, nullptr, 0);
     if (rc) return rc;
     rc = c.fetch(hr.data(), rows, sizeof(double) * hr.size());
     if (rc) return rc;
